@@ -1,0 +1,191 @@
+/* nws_b200.h — C ABI of the B200-native Neural Waveshaping Synthesis forward pass.
+ *
+ * The reference (ben-hayes/neural-waveshaping-synthesis) is pure Python/PyTorch and has no
+ * FFI of its own; its boundary for this path is the Python module API
+ *     NeuralWaveshaping.forward(f0, control)   neural_waveshaping_synthesis/models/neural_waveshaping.py:74-90
+ * and the sub-modules it calls.  Each entry point below names the reference interface it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer to fp32 (unless stated), caller-owned, borrowed for
+ *     the duration of the call; nothing is retained except by nws_load_weights/nws_set_lut,
+ *     which copy;
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; all work is enqueued on it and the
+ *     calls do not synchronise the host unless stated;
+ *   - return value 0 = NWS_OK, negative = error (nws_last_error() gives a thread-local message);
+ *   - a handle may be used from one thread at a time.
+ */
+#ifndef NWS_B200_H_
+#define NWS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NWS_API_VERSION 1
+
+enum {
+  NWS_OK = 0,
+  NWS_ERR_INVALID = -1,      /* bad argument (NULL, size, T < 2, ...)                              */
+  NWS_ERR_UNSUPPORTED = -2,  /* configuration outside what the kernels are built for               */
+  NWS_ERR_STATE = -3,        /* weights / LUT not loaded                                            */
+  NWS_ERR_CUDA = -4,         /* CUDA runtime error                                                  */
+  NWS_ERR_WORKSPACE = -5     /* workspace too small                                                 */
+};
+
+/* gin/models/newt.gin:1-33 — every hyper-parameter of the path.  The kernels are specialised
+ * for the values in the comments; nws_create rejects anything else with NWS_ERR_UNSUPPORTED.   */
+typedef struct NwsConfig {
+  int sample_rate;        /* 16000  newt.gin:1                                     */
+  int control_hop;        /* 128    newt.gin:5                                     */
+  int n_harmonics;        /* 101    newt.gin:7                                     */
+  int n_waveshapers;      /* 64     newt.gin:4                                     */
+  int embedding_size;     /* 128    newt.gin:3,16-18 (GRU hidden == embedding)     */
+  int shaping_fn_size;    /* 8      newt.gin:12                                    */
+  int shaping_fn_depth;   /* 4      newt.gin:14                                    */
+  int noise_bands;        /* 129    newt.gin:22                                    */
+  int ir_length;          /* 256    newt.gin:24                                    */
+  int reverb_length;      /* 32000  newt.gin:27-28 (length_in_seconds * sr)        */
+} NwsConfig;
+
+typedef struct NwsContext* NwsHandle;
+
+/* Order of the fp32 tensors nws_load_weights expects == state_dict() order of the reference
+ * model, native PyTorch layouts.                                           */
+enum NwsTensor {
+  NWS_T_GRU_W_IH = 0,     /* embedding.gru.weight_ih_l0          [384,2]    */
+  NWS_T_GRU_W_HH,         /* embedding.gru.weight_hh_l0          [384,128]  */
+  NWS_T_GRU_B_IH,         /* embedding.gru.bias_ih_l0            [384]      */
+  NWS_T_GRU_B_HH,         /* embedding.gru.bias_hh_l0            [384]      */
+  NWS_T_PROJ_W,           /* embedding.proj.weight               [128,128,1]*/
+  NWS_T_PROJ_B,           /* embedding.proj.bias                 [128]      */
+  NWS_T_OSC_RAND_PHASE,   /* osc.rand_phase                      [1,101,1]  */
+  NWS_T_HMIX_W,           /* harmonic_mixer.weight               [64,101,1] */
+  NWS_T_HMIX_B,           /* harmonic_mixer.bias                 [64]       */
+  NWS_T_FILM_MLP,         /* newt.mlp.net.{0,1,3,4,6,7,9}: 14 tensors in state-dict order:
+                             net.0.weight, net.0.bias, net.1.layer_norm.weight, net.1.layer_norm.bias,
+                             net.3.*, net.4.layer_norm.*, net.6.*, net.7.layer_norm.*, net.9.weight [256,128,1], net.9.bias */
+  NWS_T_SHAPER_SCALE = NWS_T_FILM_MLP + 14, /* newt.shaping_fn.input_scale [1,64,1]  */
+  NWS_T_SHAPER_W1,        /* newt.shaping_fn.net.0.weight        [512,1,1]  */
+  NWS_T_SHAPER_B1,        /* newt.shaping_fn.net.0.bias          [512]      */
+  NWS_T_SHAPER_W2,        /* newt.shaping_fn.net.2.weight        [512,8,1]  */
+  NWS_T_SHAPER_B2,
+  NWS_T_SHAPER_W3,        /* newt.shaping_fn.net.4.weight        [512,8,1]  */
+  NWS_T_SHAPER_B3,
+  NWS_T_SHAPER_W4,        /* newt.shaping_fn.net.6.weight        [64,8,1]   */
+  NWS_T_SHAPER_B4,        /* newt.shaping_fn.net.6.bias          [64]       */
+  NWS_T_MIX_W,            /* newt.mixer.0.weight                 [1,64,1]   */
+  NWS_T_MIX_B,            /* newt.mixer.0.bias                   [1]        */
+  NWS_T_NOISE_MLP,        /* h_generator.net.*: 14 tensors, same order as NWS_T_FILM_MLP, net.9 [129,128,1] */
+  NWS_T_NOISE_WINDOW = NWS_T_NOISE_MLP + 14, /* noise_synth.window [256] (must be the periodic Hann window) */
+  NWS_T_REVERB_IR,        /* reverb.ir                           [1,31999]  */
+  NWS_T_COUNT
+};
+
+/* Stage selectors for nws_stage_td_mlp. */
+enum { NWS_MLP_FILM = 0, NWS_MLP_NOISE = 1 };
+
+const char* nws_last_error(void);
+int nws_api_version(void);
+
+/* Replaces: gin-configured construction `NeuralWaveshaping()` (neural_waveshaping.py:31-62). */
+int nws_create(const NwsConfig* config, NwsHandle* out_handle);
+int nws_destroy(NwsHandle handle);
+/* Fills *config with the newt.gin values. */
+void nws_default_config(NwsConfig* config);
+
+/* Replaces: load_state_dict / `.to(device)` of the module parameters (resynthesise_dataset.py:47,53).
+ * tensors[i] is the device pointer of tensor i in NwsTensor order (n_tensors == NWS_T_COUNT).
+ * Repacks into the kernels' layouts; synchronises `stream` once (load-time only) to validate the
+ * noise window.  Invalidates the LUT and the cached reverb plans.                                 */
+int nws_load_weights(NwsHandle handle, const float* const* tensors, int n_tensors, void* stream);
+
+/* Replaces: FastNEWT._init_lookup_table (modules/shaping.py:107-119) — evaluates the 64 shaper
+ * MLPs on the table grid on the device and keeps the table.  `sample_points` (device, [table_size])
+ * is the grid, normally torch.linspace(table_min, table_max, table_size) computed by the caller
+ * exactly as the reference does; NULL -> the grid is computed on the device (may differ from
+ * torch.linspace by 1 ulp at some points).                                                        */
+int nws_build_lut(NwsHandle handle, int table_size, float table_min, float table_max,
+                  const float* sample_points, void* stream);
+/* Same, from a caller-provided table [64, table_size] (e.g. a loaded `newt.lookup_table`).        */
+int nws_set_lut(NwsHandle handle, const float* lut, int table_size, float table_min, float table_max, void* stream);
+/* Copies the current table [64, table_size] to `lut_out`. */
+int nws_get_lut(NwsHandle handle, float* lut_out, void* stream);
+
+/* Scratch the forward needs for a batch of B utterances of T control frames (bytes). */
+size_t nws_workspace_bytes(NwsHandle handle, int B, int T);
+
+/* Replaces: NeuralWaveshaping.forward (neural_waveshaping.py:74-90), eval/no-grad.
+ *   f0       [B,1,T] Hz                 control [B,ctrl_channels,T] (channels 0,1 used, :69-72)
+ *   u_phase  [101] the rand_like draw of generators.py:55, or NULL -> Philox(seed, offset)
+ *   noise    [128*T-1] the rand draw of generators.py:30, or NULL -> Philox(seed, offset)
+ *   use_lut  0 = NEWT (shaping.py:40-79), 1 = FastNEWT (shaping.py:82-151; needs a LUT)
+ *   out      [B, 128*T]
+ * T >= 2 (the reference raises for T == 1 in torch.stft's reflect padding).                       */
+int nws_forward(NwsHandle handle, const float* f0, const float* control, int ctrl_channels,
+                const float* u_phase, const float* noise, uint64_t seed, uint64_t offset,
+                float* out, int B, int T, int use_lut, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* Same path with HOST buffers (pageable or pinned): copies f0/control in, runs nws_forward,
+ * copies `out` back and synchronises `stream`.  u_phase/noise are host pointers or NULL.           */
+int nws_forward_host(NwsHandle handle, const float* f0_host, const float* control_host, int ctrl_channels,
+                     const float* u_phase_host, const float* noise_host, uint64_t seed, uint64_t offset,
+                     float* out_host, int B, int T, int use_lut, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---- stage entry points: one per row of SURVEY.md §8(a), used by the parity tests and by the
+ *      host-side sub-module mirrors.  Layouts are the reference's ([B,C,T] channel-major).        */
+
+/* get_embedding + ControlModule (neural_waveshaping.py:69-72,17-26): control -> emb [B,128,T]. */
+int nws_stage_control_embedding(NwsHandle handle, const float* control, int ctrl_channels, float* emb,
+                                int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+/* TimeDistributedMLP (modules/dynamic.py:20-40): emb [B,128,T] -> [B,256,T] (NWS_MLP_FILM,
+ * shaping.py:53-55,68) or [B,129,T] (NWS_MLP_NOISE, neural_waveshaping.py:58,82).                 */
+int nws_stage_td_mlp(NwsHandle handle, int which, const float* emb, float* out, int B, int T,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* F.upsample + render_exciter + NEWT/FastNEWT (neural_waveshaping.py:75-80, generators.py:58-66,
+ * shaping.py:67-79,136-151): f0 [B,1,T], film [B,256,T], u_phase [101] -> newt_out [B,128*T].
+ * `exciter_out` (optional, [B,64,128*T]) receives render_exciter's output for the parity tests.    */
+int nws_stage_audio(NwsHandle handle, const float* f0, const float* film, const float* u_phase,
+                    float* newt_out, float* exciter_out, int B, int T, int use_lut,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* FastNEWT.shaping_fn (shaping.py:136-151) on a materialised input: x [B,64,N] -> y [B,64,N];
+ * `lower_out` (optional, int32 [B,64,N]) receives the clamped lower table index (bit-exact target). */
+int nws_stage_lut_lookup(NwsHandle handle, const float* x, float* y, int* lower_out, int B, int N, void* stream);
+/* FIRNoiseSynth.forward (generators.py:21-35): H [B,129,T], noise [128*T-1] -> [B,128*T]. */
+int nws_stage_noise(NwsHandle handle, const float* H, const float* noise, float* out, int B, int T,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* Reverb.forward (shaping.py:161-173): x [B,N] -> out [B,N] (N any positive length). */
+int nws_stage_reverb(NwsHandle handle, const float* x, float* out, int B, int N,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* Scratch for nws_stage_reverb when N is not 128*T. */
+size_t nws_reverb_workspace_bytes(NwsHandle handle, int B, int N);
+
+/* TrainableNonlinearity on a shared grid (FastNEWT._init_lookup_table, modules/shaping.py:107-119),
+ * without a handle: shaper_tensors = the nine newt.shaping_fn tensors in state-dict order
+ * (input_scale, net.0.weight, net.0.bias, net.2.weight, net.2.bias, net.4.weight, net.4.bias,
+ * net.6.weight, net.6.bias), x [n_points] -> out [64, n_points].  scratch: device,
+ * nws_shaper_eval_scratch_bytes() bytes.                                                          */
+size_t nws_shaper_eval_scratch_bytes(void);
+int nws_shaper_eval(const float* const* shaper_tensors, const float* x, float* out, int n_points,
+                    void* scratch, void* stream);
+
+/* Per-stage device timing of nws_forward (cudaEvents on the launch stream).  Stage order:
+ * rng, phase_carry, gru, proj, film_mlp, noise_mlp, noise_spectrum, noise_filter, audio_fused, reverb. */
+#define NWS_N_STAGES 10
+int nws_set_profiling(NwsHandle handle, int enable);
+/* Waits for the recorded events and writes the last forward's stage times (ms) to ms_out[0..9]. */
+int nws_get_stage_times(NwsHandle handle, float* ms_out, int n);
+
+/* Number of kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+uint64_t nws_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NWS_B200_H_ */

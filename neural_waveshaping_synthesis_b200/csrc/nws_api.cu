@@ -1,0 +1,356 @@
+// C ABI of libnws_b200.so (include/nws_b200.h): handle management, weight loading, LUT management,
+// workspace carving and the orchestration of the forward pass
+// (NeuralWaveshaping.forward, models/neural_waveshaping.py:74-90).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nws_internal.cuh"
+
+thread_local uint64_t g_nws_launches = 0;
+static thread_local char g_err[512] = "";
+
+void nws_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* nws_last_error(void) { return g_err; }
+extern "C" int nws_api_version(void) { return NWS_API_VERSION; }
+extern "C" uint64_t nws_launch_count(int reset) {
+  const uint64_t v = g_nws_launches;
+  if (reset) g_nws_launches = 0;
+  return v;
+}
+
+extern "C" void nws_default_config(NwsConfig* c) {
+  if (!c) return;
+  c->sample_rate = kSampleRate; c->control_hop = kHop; c->n_harmonics = kHarm; c->n_waveshapers = kShapers;
+  c->embedding_size = kEmb; c->shaping_fn_size = 8; c->shaping_fn_depth = 4; c->noise_bands = kBands;
+  c->ir_length = kIr; c->reverb_length = kReverbIr;
+}
+
+extern "C" int nws_create(const NwsConfig* cfg, NwsHandle* out) {
+  if (!cfg || !out) { nws_set_error("nws_create: NULL argument"); return NWS_ERR_INVALID; }
+  NwsConfig d;
+  nws_default_config(&d);
+  if (memcmp(cfg, &d, sizeof(d)) != 0) {
+    nws_set_error("nws_create: only the gin/models/newt.gin configuration is built "
+                  "(sr 16000, hop 128, 101 harmonics, 64 shapers of width 8 depth 4, 128-d embedding, "
+                  "129 noise bands, 256-tap IR, 32000-tap reverb)");
+    return NWS_ERR_UNSUPPORTED;
+  }
+  NwsContext* ctx = new NwsContext();
+  ctx->cfg = *cfg;
+  ctx->lay = nws_packed_layout();
+  cudaError_t e = cudaGetDevice(&ctx->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->packed, (size_t)ctx->lay.total * sizeof(float));
+  if (e != cudaSuccess) {
+    nws_set_error("nws_create: %s (a CUDA device is required; there is no CPU fallback)", cudaGetErrorString(e));
+    delete ctx;
+    return NWS_ERR_CUDA;
+  }
+  int rc = nws_make_twiddle_master(ctx);
+  if (rc) { cudaFree(ctx->packed); delete ctx; return rc; }
+  *out = ctx;
+  return NWS_OK;
+}
+
+extern "C" int nws_destroy(NwsHandle ctx) {
+  if (!ctx) return NWS_OK;
+  nws_reverb_free_plans(ctx);
+  for (int i = 0; i < 2 * kStCount; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  cudaFree(ctx->packed);
+  cudaFree(ctx->lut);
+  cudaFree(ctx->tw_master);
+  delete ctx;
+  return NWS_OK;
+}
+
+extern "C" int nws_load_weights(NwsHandle ctx, const float* const* tensors, int n_tensors, void* stream) {
+  if (!ctx || !tensors) { nws_set_error("nws_load_weights: NULL argument"); return NWS_ERR_INVALID; }
+  if (n_tensors != NWS_T_COUNT) { nws_set_error("nws_load_weights: expected %d tensors, got %d", (int)NWS_T_COUNT, n_tensors); return NWS_ERR_INVALID; }
+  for (int i = 0; i < NWS_T_COUNT; ++i)
+    if (!tensors[i]) { nws_set_error("nws_load_weights: tensor %d is NULL", i); return NWS_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  // the noise branch folds the window into the spectrum analytically: it must be the periodic Hann
+  float win[kIr];
+  NWS_CUDA_OK(cudaMemcpyAsync(win, tensors[NWS_T_NOISE_WINDOW], sizeof(win), cudaMemcpyDeviceToHost, s));
+  NWS_CUDA_OK(cudaStreamSynchronize(s));
+  for (int n = 0; n < kIr; ++n) {
+    const double h = 0.5 - 0.5 * cos(2.0 * M_PI * n / kIr);
+    if (fabs((double)win[n] - h) > 1e-6) {
+      nws_set_error("nws_load_weights: noise_synth.window is not the periodic Hann window (index %d: %g vs %g)", n, win[n], h);
+      return NWS_ERR_UNSUPPORTED;
+    }
+  }
+  int rc = nws_launch_pack_weights(ctx, tensors, s);
+  if (rc) return rc;
+  ctx->weights_loaded = true;
+  ctx->lut_valid = false;
+  nws_reverb_invalidate(ctx);
+  return NWS_OK;
+}
+
+static int ensure_lut_storage(NwsContext* ctx, int table_size) {
+  if (table_size < 2 || table_size > (1 << 20)) { nws_set_error("LUT size %d out of range", table_size); return NWS_ERR_INVALID; }
+  if (ctx->lut_size != table_size) {
+    cudaFree(ctx->lut);
+    ctx->lut = nullptr;
+    ctx->lut_size = 0;
+    NWS_CUDA_OK(cudaMalloc(&ctx->lut, (size_t)kShapers * table_size * sizeof(float)));
+    ctx->lut_size = table_size;
+  }
+  return NWS_OK;
+}
+
+extern "C" int nws_build_lut(NwsHandle ctx, int table_size, float tmin, float tmax, const float* sample_points,
+                             void* stream) {
+  if (!ctx) { nws_set_error("nws_build_lut: NULL handle"); return NWS_ERR_INVALID; }
+  if (!ctx->weights_loaded) { nws_set_error("nws_build_lut: weights not loaded"); return NWS_ERR_STATE; }
+  if (!(tmax > tmin)) { nws_set_error("nws_build_lut: table_max must exceed table_min"); return NWS_ERR_INVALID; }
+  int rc = ensure_lut_storage(ctx, table_size);
+  if (rc) return rc;
+  rc = nws_launch_build_lut(ctx, sample_points, ctx->lut, table_size, tmin, tmax, (cudaStream_t)stream);
+  if (rc) return rc;
+  ctx->lut_min = tmin; ctx->lut_max = tmax; ctx->lut_valid = true;
+  return NWS_OK;
+}
+
+extern "C" int nws_set_lut(NwsHandle ctx, const float* lut, int table_size, float tmin, float tmax, void* stream) {
+  if (!ctx || !lut) { nws_set_error("nws_set_lut: NULL argument"); return NWS_ERR_INVALID; }
+  if (!(tmax > tmin)) { nws_set_error("nws_set_lut: table_max must exceed table_min"); return NWS_ERR_INVALID; }
+  int rc = ensure_lut_storage(ctx, table_size);
+  if (rc) return rc;
+  NWS_CUDA_OK(cudaMemcpyAsync(ctx->lut, lut, (size_t)kShapers * table_size * sizeof(float), cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream));
+  ctx->lut_min = tmin; ctx->lut_max = tmax; ctx->lut_valid = true;
+  return NWS_OK;
+}
+
+extern "C" int nws_get_lut(NwsHandle ctx, float* lut_out, void* stream) {
+  if (!ctx || !lut_out) { nws_set_error("nws_get_lut: NULL argument"); return NWS_ERR_INVALID; }
+  if (!ctx->lut_valid) { nws_set_error("nws_get_lut: no LUT"); return NWS_ERR_STATE; }
+  NWS_CUDA_OK(cudaMemcpyAsync(lut_out, ctx->lut, (size_t)kShapers * ctx->lut_size * sizeof(float),
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return NWS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+NwsWorkspace nws_carve_workspace(void* base, int B, int T, int fft_len) {
+  NwsWorkspace w{};
+  size_t off = 0;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += (bytes + 255) & ~(size_t)255; return r; };
+  const size_t M = (size_t)B * T, N = (size_t)T * kHop;
+  w.carry = (double*)take(M * sizeof(double));
+  w.u_phase = (float*)take(kHarmPad * sizeof(float));
+  w.noise = (float*)take(N * sizeof(float));
+  w.hbuf = (float*)take(M * kEmb * sizeof(float));
+  w.emb = (float*)take(M * kEmb * sizeof(float));
+  w.act0 = (float*)take(M * kEmb * sizeof(float));
+  w.act1 = (float*)take(M * kEmb * sizeof(float));
+  w.film = (float*)take(M * kFilm * sizeof(float));
+  w.bands = (float*)take(M * kBandsPad * sizeof(float));
+  w.xspec = (float2*)take((size_t)T * kBandsPad * sizeof(float2));
+  w.dry = (float*)take((size_t)B * N * sizeof(float));
+  w.scratch = (float*)take(M * kFilm * sizeof(float));
+  w.rev = (float2*)take((size_t)((B + 1) / 2) * fft_len * sizeof(float2));
+  w.total = off;
+  return w;
+}
+
+extern "C" size_t nws_workspace_bytes(NwsHandle ctx, int B, int T) {
+  if (!ctx || B < 1 || T < 1) return 0;
+  const int L = nws_reverb_fft_len(T * kHop);
+  if (!L) return 0;
+  return nws_carve_workspace(nullptr, B, T, L).total;
+}
+
+extern "C" size_t nws_reverb_workspace_bytes(NwsHandle ctx, int B, int N) {
+  if (!ctx || B < 1 || N < 1) return 0;
+  const int L = nws_reverb_fft_len(N);
+  if (!L) return 0;
+  return (size_t)((B + 1) / 2) * L * sizeof(float2) + 256;
+}
+
+static int check_common(NwsContext* ctx, int B, int T, void* ws, size_t ws_bytes, const char* who, NwsWorkspace* out) {
+  if (!ctx) { nws_set_error("%s: NULL handle", who); return NWS_ERR_INVALID; }
+  if (!ctx->weights_loaded) { nws_set_error("%s: weights not loaded", who); return NWS_ERR_STATE; }
+  if (B < 1) { nws_set_error("%s: batch size must be >= 1 (got %d)", who, B); return NWS_ERR_INVALID; }
+  if (T < 2) { nws_set_error("%s: T must be >= 2 control frames (got %d); the reference's STFT reflect padding has the same limit", who, T); return NWS_ERR_INVALID; }
+  if ((long long)T * kHop >= (1ll << 23)) { nws_set_error("%s: T = %d too long (phase/upsample index arithmetic is exact below 2^23 samples)", who, T); return NWS_ERR_UNSUPPORTED; }
+  const int L = nws_reverb_fft_len(T * kHop);
+  if (!L) { nws_set_error("%s: T = %d too long for the reverb FFT plan", who, T); return NWS_ERR_UNSUPPORTED; }
+  if (!ws) { nws_set_error("%s: NULL workspace", who); return NWS_ERR_INVALID; }
+  if (((uintptr_t)ws & 255) != 0) { nws_set_error("%s: workspace must be 256-byte aligned", who); return NWS_ERR_INVALID; }
+  *out = nws_carve_workspace(ws, B, T, L);
+  if (out->total > ws_bytes) { nws_set_error("%s: workspace too small (%zu < %zu bytes)", who, ws_bytes, out->total); return NWS_ERR_WORKSPACE; }
+  return NWS_OK;
+}
+
+#define NWS_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+// stage timing: events bracket each stage on the launch stream when profiling is on
+#define NWS_STAGE(ctx, st, s, expr)                                           \
+  do {                                                                        \
+    if ((ctx)->profile) cudaEventRecord((ctx)->ev[2 * (st)], (s));           \
+    NWS_TRY(expr);                                                            \
+    if ((ctx)->profile) { cudaEventRecord((ctx)->ev[2 * (st) + 1], (s)); (ctx)->ev_recorded[(st)] = true; } \
+  } while (0)
+
+extern "C" int nws_set_profiling(NwsHandle ctx, int enable) {
+  if (!ctx) { nws_set_error("nws_set_profiling: NULL handle"); return NWS_ERR_INVALID; }
+  if (enable && !ctx->ev[0]) {
+    for (int i = 0; i < 2 * kStCount; ++i) NWS_CUDA_OK(cudaEventCreate(&ctx->ev[i]));
+  }
+  ctx->profile = enable != 0;
+  for (int i = 0; i < kStCount; ++i) ctx->ev_recorded[i] = false;
+  return NWS_OK;
+}
+
+extern "C" int nws_get_stage_times(NwsHandle ctx, float* ms_out, int n) {
+  if (!ctx || !ms_out || n < kStCount) { nws_set_error("nws_get_stage_times: need room for %d floats", (int)kStCount); return NWS_ERR_INVALID; }
+  for (int i = 0; i < kStCount; ++i) {
+    ms_out[i] = 0.f;
+    if (!ctx->ev_recorded[i]) continue;
+    NWS_CUDA_OK(cudaEventSynchronize(ctx->ev[2 * i + 1]));
+    NWS_CUDA_OK(cudaEventElapsedTime(&ms_out[i], ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+  }
+  return NWS_OK;
+}
+
+extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control, int ctrl_channels,
+                           const float* u_phase, const float* noise, uint64_t seed, uint64_t offset, float* out,
+                           int B, int T, int use_lut, void* workspace, size_t workspace_bytes, void* stream) {
+  NwsWorkspace w;
+  NWS_TRY(check_common(ctx, B, T, workspace, workspace_bytes, "nws_forward", &w));
+  if (!f0 || !control || !out) { nws_set_error("nws_forward: NULL tensor"); return NWS_ERR_INVALID; }
+  if (ctrl_channels < 2) { nws_set_error("nws_forward: control needs >= 2 channels (got %d)", ctrl_channels); return NWS_ERR_INVALID; }
+  if (use_lut && !ctx->lut_valid) { nws_set_error("nws_forward: FastNEWT requested but no lookup table is loaded"); return NWS_ERR_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int M = B * T, N = T * kHop;
+
+  if (!u_phase || !noise) {  // the forward's own draws (generators.py:55, :30); injected ones are kept
+    NWS_STAGE(ctx, kStRng, s, nws_launch_rng(u_phase ? nullptr : w.u_phase, noise ? nullptr : w.noise, N - 1, seed, offset, s));
+    if (!u_phase) u_phase = w.u_phase;
+    if (!noise) noise = w.noise;
+  }
+  // hop rate: phase carries, control encoder, FiLM parameters, noise band gains
+  NWS_STAGE(ctx, kStCarry, s, nws_launch_phase_carry(f0, w.carry, B, T, s));
+  NWS_STAGE(ctx, kStGru, s, nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, s));
+  NWS_STAGE(ctx, kStProj, s, nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b,
+                                               nullptr, nullptr, w.emb, M, kEmb, kEmb, kEmb, false, s));
+  NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_td_mlp(ctx, NWS_MLP_FILM, w.emb, w.act0, w.act1, w.film, M, s));
+  NWS_STAGE(ctx, kStMlpNoise, s, nws_launch_td_mlp(ctx, NWS_MLP_NOISE, w.emb, w.act0, w.act1, w.bands, M, s));
+  // noise branch -> dry
+  NWS_STAGE(ctx, kStNoiseSpec, s, nws_launch_noise_spectrum(ctx, noise, w.xspec, T, s));
+  NWS_STAGE(ctx, kStNoiseFilter, s, nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, s));
+  // fused audio-rate kernel: dry = newt(exciter) + noise
+  NWS_STAGE(ctx, kStAudio, s, nws_launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, use_lut, s));
+  // reverb
+  NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb(ctx, w.dry, out, w.rev, B, N, s));
+  return NWS_OK;
+}
+
+extern "C" int nws_forward_host(NwsHandle ctx, const float* f0_host, const float* control_host, int ctrl_channels,
+                                const float* u_phase_host, const float* noise_host, uint64_t seed, uint64_t offset,
+                                float* out_host, int B, int T, int use_lut, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  NwsWorkspace w;
+  NWS_TRY(check_common(ctx, B, T, workspace, workspace_bytes, "nws_forward_host", &w));
+  if (!f0_host || !control_host || !out_host) { nws_set_error("nws_forward_host: NULL buffer"); return NWS_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t M = (size_t)B * T, N = (size_t)T * kHop;
+  // input staging: the layout-conversion scratch, which nws_forward itself never touches
+  float* d_f0 = w.scratch;
+  float* d_ctl = w.scratch + M;
+  if ((size_t)(1 + ctrl_channels) * M > M * kFilm) { nws_set_error("nws_forward_host: too many control channels"); return NWS_ERR_INVALID; }
+  NWS_CUDA_OK(cudaMemcpyAsync(d_f0, f0_host, M * sizeof(float), cudaMemcpyHostToDevice, s));
+  NWS_CUDA_OK(cudaMemcpyAsync(d_ctl, control_host, M * ctrl_channels * sizeof(float), cudaMemcpyHostToDevice, s));
+  const float* d_u = nullptr;
+  const float* d_n = nullptr;
+  if (u_phase_host) {
+    NWS_CUDA_OK(cudaMemcpyAsync(w.u_phase, u_phase_host, kHarm * sizeof(float), cudaMemcpyHostToDevice, s));
+    d_u = w.u_phase;
+  }
+  if (noise_host) {
+    NWS_CUDA_OK(cudaMemcpyAsync(w.noise, noise_host, (N - 1) * sizeof(float), cudaMemcpyHostToDevice, s));
+    d_n = w.noise;
+  }
+  // device-side result: the GRU state buffer is dead once the embedding is computed (long before the
+  // reverb writes its output) and has exactly B*N floats
+  float* d_out = w.hbuf;
+  NWS_TRY(nws_forward(ctx, d_f0, d_ctl, ctrl_channels, d_u, d_n, seed, offset, d_out, B, T, use_lut, workspace,
+                      workspace_bytes, stream));
+  NWS_CUDA_OK(cudaMemcpyAsync(out_host, d_out, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  NWS_CUDA_OK(cudaStreamSynchronize(s));
+  return NWS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stages
+extern "C" int nws_stage_control_embedding(NwsHandle ctx, const float* control, int ctrl_channels, float* emb, int B,
+                                           int T, void* workspace, size_t workspace_bytes, void* stream) {
+  NwsWorkspace w;
+  NWS_TRY(check_common(ctx, B, T, workspace, workspace_bytes, "nws_stage_control_embedding", &w));
+  if (!control || !emb || ctrl_channels < 2) { nws_set_error("nws_stage_control_embedding: bad argument"); return NWS_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, s));
+  NWS_TRY(nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b, nullptr, nullptr,
+                            w.emb, B * T, kEmb, kEmb, kEmb, false, s));
+  return nws_launch_rows_to_bct(w.emb, emb, B, kEmb, T, kEmb, s);
+}
+
+extern "C" int nws_stage_td_mlp(NwsHandle ctx, int which, const float* emb, float* out, int B, int T, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  NwsWorkspace w;
+  NWS_TRY(check_common(ctx, B, T, workspace, workspace_bytes, "nws_stage_td_mlp", &w));
+  if (!emb || !out || (which != NWS_MLP_FILM && which != NWS_MLP_NOISE)) { nws_set_error("nws_stage_td_mlp: bad argument"); return NWS_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  NWS_TRY(nws_launch_bct_to_rows(emb, w.emb, B, kEmb, T, kEmb, s));
+  float* dst = which == NWS_MLP_FILM ? w.film : w.bands;
+  NWS_TRY(nws_launch_td_mlp(ctx, which, w.emb, w.act0, w.act1, dst, B * T, s));
+  const int C = which == NWS_MLP_FILM ? kFilm : kBands, ld = which == NWS_MLP_FILM ? kFilm : kBandsPad;
+  return nws_launch_rows_to_bct(dst, out, B, C, T, ld, s);
+}
+
+extern "C" int nws_stage_audio(NwsHandle ctx, const float* f0, const float* film, const float* u_phase, float* newt_out,
+                               float* exciter_out, int B, int T, int use_lut, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  NwsWorkspace w;
+  NWS_TRY(check_common(ctx, B, T, workspace, workspace_bytes, "nws_stage_audio", &w));
+  if (!f0 || !film || !u_phase || !newt_out) { nws_set_error("nws_stage_audio: NULL tensor"); return NWS_ERR_INVALID; }
+  if (use_lut && !ctx->lut_valid) { nws_set_error("nws_stage_audio: no lookup table"); return NWS_ERR_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  NWS_TRY(nws_launch_bct_to_rows(film, w.film, B, kFilm, T, kFilm, s));
+  NWS_TRY(nws_launch_phase_carry(f0, w.carry, B, T, s));
+  return nws_launch_audio(ctx, f0, w.carry, w.film, u_phase, nullptr, newt_out, exciter_out, B, T, use_lut, s);
+}
+
+extern "C" int nws_stage_noise(NwsHandle ctx, const float* H, const float* noise, float* out, int B, int T,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  NwsWorkspace w;
+  NWS_TRY(check_common(ctx, B, T, workspace, workspace_bytes, "nws_stage_noise", &w));
+  if (!H || !noise || !out) { nws_set_error("nws_stage_noise: NULL tensor"); return NWS_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  NWS_TRY(nws_launch_bct_to_rows(H, w.bands, B, kBands, T, kBandsPad, s));
+  NWS_TRY(nws_launch_noise_spectrum(ctx, noise, w.xspec, T, s));
+  return nws_launch_noise_filter(ctx, w.bands, w.xspec, out, B, T, s);
+}
+
+extern "C" int nws_stage_reverb(NwsHandle ctx, const float* x, float* out, int B, int N, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (!ctx || !x || !out || !workspace) { nws_set_error("nws_stage_reverb: NULL argument"); return NWS_ERR_INVALID; }
+  if (!ctx->weights_loaded) { nws_set_error("nws_stage_reverb: weights not loaded"); return NWS_ERR_STATE; }
+  if (B < 1 || N < 1) { nws_set_error("nws_stage_reverb: bad shape"); return NWS_ERR_INVALID; }
+  const size_t need = nws_reverb_workspace_bytes(ctx, B, N);
+  if (!need) { nws_set_error("nws_stage_reverb: N = %d too long", N); return NWS_ERR_UNSUPPORTED; }
+  if (workspace_bytes < need) { nws_set_error("nws_stage_reverb: workspace too small (%zu < %zu)", workspace_bytes, need); return NWS_ERR_WORKSPACE; }
+  float2* work = (float2*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  return nws_launch_reverb(ctx, x, out, work, B, N, (cudaStream_t)stream);
+}

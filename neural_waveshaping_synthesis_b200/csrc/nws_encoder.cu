@@ -1,0 +1,309 @@
+// Hop-rate part of the NWS forward: fp64 phase carries, the control encoder (GRU + 1x1 conv)
+// and the two TimeDistributedMLPs.  Reference: models/neural_waveshaping.py:17-26,69-72,75;
+// modules/dynamic.py:11-40; modules/generators.py:59 (cumsum).
+//
+// Layout: every hop-rate activation is frame-major, X[(b*T + t)][channel] — one frame's channels
+// are contiguous so a 128-sample audio tile later reads its three frames as three 1 KB rows.
+#include "nws_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// carry[b][t] = sum over hops t' < t of sum_{n in hop t'} double(f0_up[n])   (generators.py:59:
+// torch's CPU cumsum accumulates float32 inputs in double and rounds each output to float32; the
+// audio kernel adds the in-hop fp64 prefix to this carry and rounds once).
+__global__ void __launch_bounds__(128) nws_phase_carry_kernel(const float* __restrict__ f0, double* __restrict__ carry,
+                                                              int T) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* f = f0 + (size_t)b * T;
+  const float inv_hop = (float)T / (float)(T * kHop);
+  __shared__ double warp_tot[4];
+  __shared__ double chunk_tot;
+  double base = 0.0;
+  for (int t0 = 0; t0 < T; t0 += 128) {
+    const int t = t0 + tid;
+    double s = 0.0;
+    if (t < T) {
+      const float fm = f[t > 0 ? t - 1 : 0], fc = f[t], fp = f[t + 1 < T ? t + 1 : T - 1];
+      for (int r = 0; r < kHop; ++r) {
+        const NwsLerp c = nws_lerp_coords(t * kHop + r, T, inv_hop);
+        const float x0 = c.i0 == t ? fc : (c.i0 < t ? fm : fp);
+        const float x1 = c.i1 == t ? fc : (c.i1 < t ? fm : fp);
+        s += (double)nws_lerp_apply(c, x0, x1);
+      }
+    }
+    double v = s;  // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    double pre = 0.0;
+    for (int w = 0; w < warp; ++w) pre += warp_tot[w];
+    if (t < T) carry[(size_t)b * T + t] = base + pre + (v - s);
+    if (tid == 127) chunk_tot = pre + v;
+    __syncthreads();
+    base += chunk_tot;
+    __syncthreads();
+  }
+}
+
+int nws_launch_phase_carry(const float* f0, double* carry, int B, int T, cudaStream_t s) {
+  nws_phase_carry_kernel<<<B, 128, 0, s>>>(f0, carry, T);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GRU(2 -> 128), h0 = 0, gate order r,z,n (neural_waveshaping.py:21,25).
+// One CTA per utterance, one thread per gate row: the thread keeps its W_hh row (128 floats) in
+// registers for all T steps, h lives in shared memory.  The recurrence is the only sequential
+// dependency at hop rate; 384 threads x 128 FMAs per step.
+__device__ __forceinline__ float nws_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(kGates, 1)
+nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, const float* __restrict__ b_ih,
+               const float* __restrict__ b_hh, const float* __restrict__ control, int ctrl_channels,
+               float* __restrict__ hbuf, int T) {
+  const int b = blockIdx.x, r = threadIdx.x;
+  __shared__ __align__(16) float h_s[2][kEmb];
+  __shared__ float pre_rz[2 * kEmb];
+  __shared__ float pre_ni[kEmb], pre_nh[kEmb];
+
+  float w[kEmb];
+#pragma unroll
+  for (int k = 0; k < kEmb; k += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(w_hh + (size_t)r * kEmb + k);
+    w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
+  }
+  const float wi0 = w_ih[r * 2], wi1 = w_ih[r * 2 + 1], bi = b_ih[r], bh = b_hh[r];
+  const float* c0 = control + (size_t)b * ctrl_channels * T;
+  const float* c1 = c0 + T;
+  if (r < kEmb) h_s[0][r] = 0.0f;
+  float x0 = c0[0], x1 = c1[0];
+  __syncthreads();
+
+  for (int t = 0; t < T; ++t) {
+    const float* h = h_s[t & 1];
+    const float nx0 = t + 1 < T ? c0[t + 1] : 0.0f, nx1 = t + 1 < T ? c1[t + 1] : 0.0f;  // prefetch
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kEmb; k += 8) {
+      const float4 p = *reinterpret_cast<const float4*>(h + k);
+      const float4 q = *reinterpret_cast<const float4*>(h + k + 4);
+      a0 = fmaf(w[k], p.x, a0); a1 = fmaf(w[k + 1], p.y, a1); a2 = fmaf(w[k + 2], p.z, a2); a3 = fmaf(w[k + 3], p.w, a3);
+      a4 = fmaf(w[k + 4], q.x, a4); a5 = fmaf(w[k + 5], q.y, a5); a6 = fmaf(w[k + 6], q.z, a6); a7 = fmaf(w[k + 7], q.w, a7);
+    }
+    const float gh = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) + bh;
+    const float gi = fmaf(wi1, x1, fmaf(wi0, x0, bi));
+    if (r < 2 * kEmb) {
+      pre_rz[r] = gi + gh;
+    } else {
+      pre_ni[r - 2 * kEmb] = gi;
+      pre_nh[r - 2 * kEmb] = gh;
+    }
+    __syncthreads();
+    if (r < kEmb) {
+      const float rg = nws_sigmoid(pre_rz[r]);
+      const float zg = nws_sigmoid(pre_rz[kEmb + r]);
+      const float ng = tanhf(fmaf(rg, pre_nh[r], pre_ni[r]));
+      const float hn = fmaf(zg, h[r] - ng, ng);  // (1-z)*n + z*h
+      h_s[(t + 1) & 1][r] = hn;
+      hbuf[((size_t)b * T + t) * kEmb + r] = hn;
+    }
+    x0 = nx0; x1 = nx1;
+    __syncthreads();
+  }
+}
+
+int nws_launch_gru(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, int B, int T,
+                   cudaStream_t s) {
+  const float* p = ctx->packed;
+  nws_gru_kernel<<<B, kGates, 0, s>>>(p + ctx->lay.gru_whh, p + ctx->lay.gru_wih, p + ctx->lay.gru_bih,
+                                      p + ctx->lay.gru_bhh, control, ctrl_channels, hbuf, T);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Y[M x n_out] = X[M x 128] . Wt[128 x ldw] + bias, optionally followed by LayerNorm(128, eps 1e-5)
+// and LeakyReLU(0.01) — one Conv1d(k=1) [+ TimeDistributedLayerNorm + LeakyReLU] of
+// modules/dynamic.py:28-37 on frame-major activations.  CTA tile 64 frames x 128 outputs, 256
+// threads, each 4 frames x 8 outputs; fp32 FMA (3xTF32 tensor-core version: see DESIGN.md roadmap).
+constexpr int kLinFrames = 64;
+constexpr int kLinXs = kEmb + 4;  // padded row of the X tile
+
+template <bool LN_ACT>
+__global__ void __launch_bounds__(256, 2)
+nws_linear128_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const float* __restrict__ bias,
+                     const float* __restrict__ ln_g, const float* __restrict__ ln_b, float* __restrict__ Y, int M,
+                     int n_out, int ldw, int ldy) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;                    // [128][128]
+  float* Xs = smem + kEmb * kEmb;      // [64][132]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * kLinFrames, n0 = blockIdx.y * 128;
+
+  for (int i = tid; i < kEmb * 32; i += 256) {  // weights: 128 rows x 32 float4
+    const int k = i >> 5, c4 = (i & 31) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + c4 < ldw) v = *reinterpret_cast<const float4*>(Wt + (size_t)k * ldw + n0 + c4);
+    *reinterpret_cast<float4*>(Ws + k * kEmb + c4) = v;
+  }
+  for (int i = tid; i < kLinFrames * 32; i += 256) {
+    const int f = i >> 5, c4 = (i & 31) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + f < M) v = *reinterpret_cast<const float4*>(X + (size_t)(m0 + f) * kEmb + c4);
+    *reinterpret_cast<float4*>(Xs + f * kLinXs + c4) = v;
+  }
+  __syncthreads();
+
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+#pragma unroll 2
+  for (int k4 = 0; k4 < kEmb; k4 += 4) {
+    float4 xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty * 4 + i) * kLinXs + k4);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 wa = *reinterpret_cast<const float4*>(Ws + (k4 + kk) * kEmb + tx * 4);
+      const float4 wb = *reinterpret_cast<const float4*>(Ws + (k4 + kk) * kEmb + 64 + tx * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
+        acc[i][0] = fmaf(x, wa.x, acc[i][0]); acc[i][1] = fmaf(x, wa.y, acc[i][1]);
+        acc[i][2] = fmaf(x, wa.z, acc[i][2]); acc[i][3] = fmaf(x, wa.w, acc[i][3]);
+        acc[i][4] = fmaf(x, wb.x, acc[i][4]); acc[i][5] = fmaf(x, wb.y, acc[i][5]);
+        acc[i][6] = fmaf(x, wb.z, acc[i][6]); acc[i][7] = fmaf(x, wb.w, acc[i][7]);
+      }
+    }
+  }
+
+  float bv[8], gv[8], bev[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+    bv[j] = col < n_out ? bias[col] : 0.f;
+    if (LN_ACT) { gv[j] = ln_g[col]; bev[j] = ln_b[col]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[i][j] + bv[j];
+    if (LN_ACT) {
+      // LayerNorm over the 128 channels of this frame: 16 threads (one half-warp) hold 8 each
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.0f / kEmb);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = 1.0f / sqrtf(q * (1.0f / kEmb) + 1e-5f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = fmaf((v[j] - mean) * rstd, gv[j], bev[j]);
+        v[j] = y > 0.f ? y : 0.01f * y;
+      }
+    }
+    const int m = m0 + ty * 4 + i;
+    if (m < M) {
+      float* yr = Y + (size_t)m * ldy + n0;
+      if (n0 + tx * 4 + 3 < ldy) *reinterpret_cast<float4*>(yr + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      if (n0 + 64 + tx * 4 + 3 < ldy) *reinterpret_cast<float4*>(yr + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+int nws_launch_linear(const float* X, const float* Wt, const float* bias, const float* ln_g, const float* ln_b,
+                      float* Y, int M, int n_out, int ldw, int ldy, bool ln_act, cudaStream_t s) {
+  const size_t smem = (size_t)(kEmb * kEmb + kLinFrames * kLinXs) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_linear128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_linear128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((M + kLinFrames - 1) / kLinFrames, (ldy + 127) / 128);
+  if (ln_act) {
+    if (n_out != kEmb) { nws_set_error("LayerNorm epilogue needs n_out == 128"); return NWS_ERR_INVALID; }
+    nws_linear128_kernel<true><<<grid, 256, smem, s>>>(X, Wt, bias, ln_g, ln_b, Y, M, n_out, ldw, ldy);
+  } else {
+    nws_linear128_kernel<false><<<grid, 256, smem, s>>>(X, Wt, bias, nullptr, nullptr, Y, M, n_out, ldw, ldy);
+  }
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}
+
+// TimeDistributedMLP, depth 4 (shaping.py:53-55 / neural_waveshaping.py:58 with newt.gin:20-23).
+int nws_launch_td_mlp(const NwsContext* ctx, int which, const float* emb, float* act0, float* act1, float* out, int M,
+                      cudaStream_t s) {
+  const NwsTdMlpOffsets& o = ctx->lay.mlp[which];
+  const float* p = ctx->packed;
+  const float* in = emb;
+  float* bufs[2] = {act0, act1};
+  for (int l = 0; l < 3; ++l) {
+    float* dst = bufs[l & 1];
+    int rc = nws_launch_linear(in, p + o.wt[l], p + o.b[l], p + o.g[l], p + o.beta[l], dst, M, kEmb, kEmb, kEmb, true, s);
+    if (rc) return rc;
+    in = dst;
+  }
+  const int n_out = which == NWS_MLP_FILM ? kFilm : kBands;
+  return nws_launch_linear(in, p + o.wt_out, p + o.b_out, nullptr, nullptr, out, M, n_out, o.ld_out, o.ld_out, false, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout conversion for the stage entry points: reference [B,C,T] <-> frame-major rows [B*T][ld].
+__global__ void nws_bct_to_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T, int ld) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? in[((size_t)b * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < T && c < ld) out[((size_t)b * T + t) * ld + c] = c < C ? tile[tx][i] : 0.f;
+  }
+}
+
+__global__ void nws_rows_to_bct_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T, int ld) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    tile[i][tx] = (c < C && t < T) ? in[((size_t)b * T + t) * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (c < C && t < T) out[((size_t)b * C + c) * T + t] = tile[tx][i];
+  }
+}
+
+int nws_launch_bct_to_rows(const float* in, float* out, int B, int C, int T, int ld_out, cudaStream_t s) {
+  dim3 grid((T + 31) / 32, (ld_out + 31) / 32, B), block(32, 8);
+  nws_bct_to_rows_kernel<<<grid, block, 0, s>>>(in, out, C, T, ld_out);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}
+
+int nws_launch_rows_to_bct(const float* in, float* out, int B, int C, int T, int ld_in, cudaStream_t s) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  nws_rows_to_bct_kernel<<<grid, block, 0, s>>>(in, out, C, T, ld_in);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}

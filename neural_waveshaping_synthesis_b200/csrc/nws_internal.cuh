@@ -1,0 +1,184 @@
+// Internal declarations shared by the .cu files of libnws_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nws_b200.h"
+#include "nws_math.h"
+
+// ------------------------------------------------------------------ fixed sizes (gin/models/newt.gin)
+constexpr int kSampleRate = 16000;
+constexpr int kHop = 128;
+constexpr int kHarm = 101;
+constexpr int kHarmPad = 104;          // harmonic axis padded to a multiple of 8 (zero weights)
+constexpr int kShapers = 64;
+constexpr int kEmb = 128;
+constexpr int kGates = 3 * kEmb;       // GRU rows, order r,z,n (torch.nn.GRU)
+constexpr int kFilm = 4 * kShapers;    // gamma_index, beta_index, gamma_norm, beta_norm
+constexpr int kBands = 129;
+constexpr int kBandsPad = 132;         // row stride of the noise-band / spectrum arrays (16 B multiple)
+constexpr int kIr = 256;
+constexpr int kReverbIr = 32000;       // [0, ir] (shaping.py:162)
+constexpr int kShaperStride = 176;     // packed floats per shaper (172 used)
+
+// packed per-shaper record (floats): all vector groups 16-byte aligned
+constexpr int kShpScale = 0, kShpB4 = 1, kShpW1 = 4, kShpB1 = 12, kShpW2 = 20, kShpB2 = 84, kShpW3 = 92,
+              kShpB3 = 156, kShpW4 = 164;
+
+// ------------------------------------------------------------------ packed weight blob (float offsets)
+struct NwsTdMlpOffsets {
+  int wt[3], b[3], g[3], beta[3];  // hidden layers: wt [128][128] k-major, bias, LN gamma/beta
+  int wt_out, b_out, ld_out;       // output layer: wt [128][ld_out] k-major (zero padded), bias [ld_out]
+};
+
+struct NwsPackedLayout {
+  int gru_whh, gru_wih, gru_bih, gru_bhh;
+  int proj_wt, proj_b;
+  NwsTdMlpOffsets mlp[2];
+  int hmix_wt, hmix_b;             // [kHarmPad][64] k-major, [64]
+  int shaper;                      // [64][kShaperStride]
+  int mix_w, mix_b;
+  int rand_phase;                  // [kHarmPad]
+  int ir;                          // [kReverbIr]  ([0, ir])
+  int total;
+};
+
+inline NwsPackedLayout nws_packed_layout() {
+  NwsPackedLayout L{};
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  L.gru_whh = take(kGates * kEmb);
+  L.gru_wih = take(kGates * 2);
+  L.gru_bih = take(kGates);
+  L.gru_bhh = take(kGates);
+  L.proj_wt = take(kEmb * kEmb);
+  L.proj_b = take(kEmb);
+  for (int m = 0; m < 2; ++m) {
+    for (int l = 0; l < 3; ++l) {
+      L.mlp[m].wt[l] = take(kEmb * kEmb);
+      L.mlp[m].b[l] = take(kEmb);
+      L.mlp[m].g[l] = take(kEmb);
+      L.mlp[m].beta[l] = take(kEmb);
+    }
+    L.mlp[m].ld_out = m == 0 ? kFilm : kBandsPad;
+    L.mlp[m].wt_out = take(kEmb * L.mlp[m].ld_out);
+    L.mlp[m].b_out = take(L.mlp[m].ld_out);
+  }
+  L.hmix_wt = take(kHarmPad * kShapers);
+  L.hmix_b = take(kShapers);
+  L.shaper = take(kShapers * kShaperStride);
+  L.mix_w = take(kShapers);
+  L.mix_b = take(4);
+  L.rand_phase = take(kHarmPad);
+  L.ir = take(kReverbIr);
+  L.total = o;
+  return L;
+}
+
+// ------------------------------------------------------------------ reverb FFT plan
+struct NwsReverbPlan {
+  int n1 = 0, log_n1 = 0;      // column FFT length; L = n1 * 256
+  int cols_per_cta = 0;        // W
+  float2* tw_big = nullptr;    // [L]   exp(-2*pi*i*n2*k1/L) at index k1*256+n2
+  float2* ir_spec = nullptr;   // [L]   spectrum of [0, ir] in the four-step layout
+  bool ir_valid = false;
+};
+
+constexpr int kMaxPlans = 8;
+constexpr int kTwMaster = 4096;  // master twiddle table: W_4096^m, m < 2048
+
+struct NwsContext {
+  NwsConfig cfg;
+  NwsPackedLayout lay;
+  float* packed = nullptr;     // device weight blob
+  bool weights_loaded = false;
+  float* lut = nullptr;        // [64][table_size]
+  int lut_size = 0;
+  float lut_min = 0.f, lut_max = 0.f;
+  bool lut_valid = false;
+  float2* tw_master = nullptr; // [kTwMaster/2]
+  NwsReverbPlan plans[kMaxPlans];
+  int n_plans = 0;
+  int sm_count = 148;
+  int device = 0;
+  // optional per-stage timing of nws_forward (cudaEvents on the launch stream)
+  bool profile = false;
+  cudaEvent_t ev[2 * 10] = {};
+  bool ev_recorded[10] = {};
+};
+
+enum { kStRng = 0, kStCarry, kStGru, kStProj, kStMlpFilm, kStMlpNoise, kStNoiseSpec, kStNoiseFilter, kStAudio, kStReverb, kStCount };
+
+// ------------------------------------------------------------------ workspace carving
+struct NwsWorkspace {
+  double* carry;      // [B*T]   exclusive fp64 prefix of per-hop f0 sums
+  float* u_phase;     // [kHarmPad]
+  float* noise;       // [128*T]
+  float* hbuf;        // [M][128] GRU states
+  float* emb;         // [M][128]
+  float* act0;        // [M][128]
+  float* act1;        // [M][128]
+  float* film;        // [M][256]
+  float* bands;       // [M][kBandsPad]
+  float2* xspec;      // [T][kBandsPad]
+  float* dry;         // [B][N]
+  float* scratch;     // [M][256]  layout conversion for the stage entry points
+  float2* rev;        // [ceil(B/2)][L]
+  size_t total;
+};
+
+NwsWorkspace nws_carve_workspace(void* base, int B, int T, int fft_len);
+int nws_reverb_fft_len(int N);  // L = n1*256 >= N + kReverbIr - 1, n1 a power of two >= 128; 0 if unsupported
+
+// ------------------------------------------------------------------ error / launch bookkeeping
+void nws_set_error(const char* fmt, ...);
+extern thread_local uint64_t g_nws_launches;
+
+#define NWS_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      nws_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return NWS_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define NWS_LAUNCH_CHECK()                                                                  \
+  do {                                                                                      \
+    ++g_nws_launches;                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      nws_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return NWS_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+// ------------------------------------------------------------------ kernel launchers (one per .cu)
+// nws_encoder.cu
+int nws_launch_phase_carry(const float* f0, double* carry, int B, int T, cudaStream_t s);
+int nws_launch_gru(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, int B, int T, cudaStream_t s);
+int nws_launch_linear(const float* X, const float* Wt, const float* bias, const float* ln_g, const float* ln_b,
+                      float* Y, int M, int n_out, int ldw, int ldy, bool ln_act, cudaStream_t s);
+int nws_launch_td_mlp(const NwsContext* ctx, int which, const float* emb, float* act0, float* act1, float* out,
+                      int M, cudaStream_t s);
+int nws_launch_bct_to_rows(const float* in, float* out, int B, int C, int T, int ld_out, cudaStream_t s);
+int nws_launch_rows_to_bct(const float* in, float* out, int B, int C, int T, int ld_in, cudaStream_t s);
+// nws_audio.cu
+int nws_launch_rng(float* u_phase, float* noise, int n_noise, uint64_t seed, uint64_t offset, cudaStream_t s);
+int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
+                     const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
+                     int use_lut, cudaStream_t s);
+int nws_launch_build_lut(const NwsContext* ctx, const float* points, float* lut, int table_size, float tmin,
+                         float tmax, cudaStream_t s);
+int nws_launch_pack_weights(NwsContext* ctx, const float* const* tensors, cudaStream_t s);
+// nws_noise.cu
+int nws_launch_noise_spectrum(const NwsContext* ctx, const float* noise, float2* xspec, int T, cudaStream_t s);
+int nws_launch_noise_filter(const NwsContext* ctx, const float* bands, const float2* xspec, float* out, int B, int T,
+                            cudaStream_t s);
+// nws_reverb.cu
+int nws_reverb_get_plan(NwsContext* ctx, int fft_len, cudaStream_t s, NwsReverbPlan** out);
+int nws_launch_reverb(NwsContext* ctx, const float* x, float* out, float2* work, int B, int N, cudaStream_t s);
+void nws_reverb_free_plans(NwsContext* ctx);
+void nws_reverb_invalidate(NwsContext* ctx);
+int nws_make_twiddle_master(NwsContext* ctx);

@@ -1,0 +1,132 @@
+// Filtered-noise branch: FIRNoiseSynth.forward (modules/generators.py:21-35).
+//
+// The reference designs a zero-phase IR per frame (irfft of the 129 real band gains -> roll 128 ->
+// periodic Hann), takes its rfft, multiplies the STFT of one shared uniform-noise vector
+// (n_fft 256, hop 128, centre + reflect padding, rectangular window) and inverts with
+// istft(center=False).  Two identities make this cheap without changing the result:
+//   * roll by 128 multiplies bin k by (-1)^k and the Hann window is a 3-tap filter across bins, so
+//     rfft(roll(irfft(H)) * hann)[k] = (-1)^k (0.5 H[k] + 0.25 (H[k-1] + H[k+1]))  (H even-extended)
+//     — a REAL response: no transform is needed for the IR design;
+//   * two real 256-point frames share one complex FFT (frame a in the real part, b in the imaginary).
+// istft with a rectangular window is overlap-add divided by the frame-count envelope {1,2}.
+#include "nws_fft.cuh"
+#include "nws_internal.cuh"
+
+__device__ __forceinline__ void nws_load_tw256(float2* tw_s, const float2* __restrict__ tw_master, int tid, int nthreads) {
+  for (int i = tid; i < 128; i += nthreads) tw_s[i] = tw_master[i * (kTwMaster / 256)];
+}
+
+// X[t][k] = rfft(xp[128 t : 128 t + 256])[k], xp = reflect_pad(noise, 128)   (generators.py:31).
+// One CTA per pair of frames.
+__global__ void __launch_bounds__(128) nws_noise_spectrum_kernel(const float* __restrict__ noise, int n_noise,
+                                                                 const float2* __restrict__ tw_master,
+                                                                 float2* __restrict__ xspec, int T) {
+  __shared__ float2 buf_a[256], buf_b[256], tw_s[128];
+  const int tid = threadIdx.x, ta = 2 * blockIdx.x, tb = ta + 1;
+  nws_load_tw256(tw_s, tw_master, tid, 128);
+  for (int n = tid; n < 256; n += 128) {
+    float v[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int t = q == 0 ? ta : tb;
+      int idx = t * kHop + n - kIr / 2;               // index into the unpadded noise
+      if (idx < 0) idx = -idx;                        // reflect (no edge repeat)
+      if (idx >= n_noise) idx = 2 * (n_noise - 1) - idx;
+      v[q] = t < T ? noise[idx] : 0.f;
+    }
+    buf_a[n] = make_float2(v[0], v[1]);
+  }
+  __syncthreads();
+  const float2* z = nws_fft_smem<false, false>(buf_a, buf_b, tw_s, 1, 8, 1, tid, 128);
+  for (int k = tid; k <= 128; k += 128) {
+    const float2 zk = z[k], zc = z[(256 - k) & 255];
+    // Xa = (Z[k] + conj(Z[N-k])) / 2 ; Xb = (Z[k] - conj(Z[N-k])) / (2i)
+    const float2 xa = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+    const float2 xb = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+    xspec[(size_t)ta * kBandsPad + k] = xa;
+    if (tb < T) xspec[(size_t)tb * kBandsPad + k] = xb;
+  }
+}
+
+int nws_launch_noise_spectrum(const NwsContext* ctx, const float* noise, float2* xspec, int T, cudaStream_t s) {
+  nws_noise_spectrum_kernel<<<(T + 1) / 2, 128, 0, s>>>(noise, kHop * T - 1, ctx->tw_master, xspec, T);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}
+
+// One CTA = one utterance x kNoiseHops output hops.  It filters frames t0-1 .. t0+kNoiseHops-1
+// (kNoiseHops+1 frames = (kNoiseHops+1)/2 complex FFTs, two at a time), keeps their 256-sample
+// outputs in shared memory and overlap-adds them into the kNoiseHops hops it owns.
+constexpr int kNoiseHops = 15;
+constexpr int kNoiseFrames = kNoiseHops + 1;
+
+__global__ void __launch_bounds__(256) nws_noise_filter_kernel(const float* __restrict__ bands,
+                                                               const float2* __restrict__ xspec,
+                                                               const float2* __restrict__ tw_master,
+                                                               float* __restrict__ out, int T) {
+  __shared__ float2 buf_a[2][256], buf_b[2][256], tw_s[128];
+  __shared__ float hs[2][2][kBandsPad];           // [fft][frame of pair][band]
+  __shared__ float y_s[kNoiseFrames][256];
+  const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kNoiseHops;
+  const int g = tid >> 7, j = tid & 127;          // g: which of the two concurrent FFTs
+  nws_load_tw256(tw_s, tw_master, tid, 256);
+
+  for (int pair0 = 0; pair0 < kNoiseFrames / 2; pair0 += 2) {
+    const int pair = pair0 + g;
+    const int fa = t0 - 1 + 2 * pair, fb = fa + 1;  // frame indices of this FFT's pair
+    __syncthreads();
+    for (int q = 0; q < 2; ++q) {
+      const int f = q == 0 ? fa : fb;
+      for (int k = j; k < kBandsPad; k += 128)
+        hs[g][q][k] = (f >= 0 && f < T && k < kBands) ? bands[((size_t)b * T + f) * kBandsPad + k] : 0.f;
+    }
+    __syncthreads();
+    // Z[k] = Ya[k] + i Yb[k], Y = X * Hw, Hermitian-extended to 256 bins
+    for (int k = j; k < 256; k += 128) {
+      const int kk = k <= 128 ? k : 256 - k;
+      const int km = kk == 0 ? 1 : kk - 1, kp = kk == 128 ? 127 : kk + 1;
+      const float sgn = (kk & 1) ? -1.f : 1.f;
+      float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
+      if (fa >= 0 && fa < T) {
+        const float hw = sgn * fmaf(0.25f, hs[g][0][km] + hs[g][0][kp], 0.5f * hs[g][0][kk]);
+        const float2 x = xspec[(size_t)fa * kBandsPad + kk];
+        ya = make_float2(x.x * hw, x.y * hw);
+      }
+      if (fb >= 0 && fb < T) {
+        const float hw = sgn * fmaf(0.25f, hs[g][1][km] + hs[g][1][kp], 0.5f * hs[g][1][kk]);
+        const float2 x = xspec[(size_t)fb * kBandsPad + kk];
+        yb = make_float2(x.x * hw, x.y * hw);
+      }
+      if (kk == 0 || kk == 128) { ya.y = 0.f; yb.y = 0.f; }  // irfft ignores the imaginary part of DC / Nyquist
+      if (k > 128) { ya.y = -ya.y; yb.y = -yb.y; }            // conj for the mirrored half
+      buf_a[g][k] = make_float2(ya.x - yb.y, ya.y + yb.x);
+    }
+    __syncthreads();
+    // both FFTs advance in lock-step (the helper's barriers are CTA-wide)
+    const float2* z = nws_fft_smem<true, false>(&buf_a[0][0], &buf_b[0][0], tw_s, 1, 8, 2, tid, 256);
+    for (int n = j; n < 256; n += 128) {
+      const float2 v = z[g * 256 + n];
+      y_s[2 * pair][n] = v.x * (1.0f / 256.0f);
+      y_s[2 * pair + 1][n] = v.y * (1.0f / 256.0f);
+    }
+  }
+  __syncthreads();
+  // overlap-add: hop t takes the first half of frame t and the second half of frame t-1, divided by
+  // the number of overlapping frames (1 in the first hop, else 2)
+  const int N = T * kHop;
+  for (int i = tid; i < kNoiseHops * kHop; i += 256) {
+    const int h = i >> 7, r = i & 127, t = t0 + h;
+    if (t >= T) break;
+    const float cur = y_s[h + 1][r];
+    const float v = t == 0 ? cur : 0.5f * (y_s[h][kHop + r] + cur);
+    out[(size_t)b * N + t * kHop + r] = v;
+  }
+}
+
+int nws_launch_noise_filter(const NwsContext* ctx, const float* bands, const float2* xspec, float* out, int B, int T,
+                            cudaStream_t s) {
+  dim3 grid((T + kNoiseHops - 1) / kNoiseHops, B);
+  nws_noise_filter_kernel<<<grid, 256, 0, s>>>(bands, xspec, ctx->tw_master, out, T);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}

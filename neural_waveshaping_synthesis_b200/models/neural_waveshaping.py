@@ -1,0 +1,199 @@
+"""Drop-in `NeuralWaveshaping` — host-side mirror of the reference's
+models/neural_waveshaping.py (ControlModule :17-26, NeuralWaveshaping :29-90).
+
+Same gin-configurable names, constructor arguments, sub-module names and state-dict keys, so
+`gin.parse_config_file(...); NeuralWaveshaping()`, `load_from_checkpoint`, `model.newt =
+FastNEWT(model.newt)`, `.eval()`, `.to(device)` and `model(f0, control)` behave as the reference
+scripts expect (scripts/time_forward_pass.py:41-51, time_buffer_sizes.py:35-68,
+resynthesise_dataset.py:47-59).  `forward` runs entirely in libnws_b200.so (hand-written sm_100a
+CUDA behind the C ABI in include/nws_b200.h); it requires a CUDA device — there is no CPU path.
+
+Training (the reference's LightningModule steps, :92-165) is out of scope.
+"""
+import pickle
+
+import gin
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..engine import NwsEngine
+from .modules._bound import BoundToRoot
+from .modules.dynamic import TimeDistributedMLP
+from .modules.generators import FIRNoiseSynth, HarmonicOscillator
+from .modules.shaping import NEWT, FastNEWT, Reverb
+
+gin.external_configurable(nn.GRU, module="torch.nn")
+gin.external_configurable(nn.Conv1d, module="torch.nn")
+
+
+@gin.configurable
+class ControlModule(nn.Module, BoundToRoot):
+    """GRU(control_size -> hidden) over frames, then a 1x1 convolution to the embedding."""
+
+    def __init__(self, control_size: int, hidden_size: int, embedding_size: int):
+        super().__init__()
+        self.gru = nn.GRU(control_size, hidden_size, batch_first=True)
+        self.proj = nn.Conv1d(hidden_size, embedding_size, 1)
+
+    def forward(self, x):
+        return self._root()._engine_for(x).control_embedding(x)
+
+
+class _PermissiveUnpickler(pickle.Unpickler):
+    """Lightning checkpoints pickle classes (ModelCheckpoint, AttributeDict) that need not be
+    installed; only `state_dict` and `hyper_parameters` are read, so unknown classes become dicts."""
+
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except Exception:
+            return type(name, (dict,), {"__module__": module, "__hash__": lambda self: id(self),
+                                        "__setstate__": lambda self, state: None})
+
+
+class _PermissivePickle:
+    __name__ = "nws_permissive_pickle"
+    Unpickler = _PermissiveUnpickler
+
+    @staticmethod
+    def load(f, **kw):
+        return _PermissiveUnpickler(f, **kw).load()
+
+
+@gin.configurable
+class NeuralWaveshaping(nn.Module):
+    def __init__(self, n_waveshapers: int, control_hop: int, sample_rate: float = 16000,
+                 learning_rate: float = 1e-3, lr_decay: float = 0.9, lr_decay_interval: int = 10000,
+                 log_audio: bool = False):
+        super().__init__()
+        self.hparams = dict(n_waveshapers=n_waveshapers, control_hop=control_hop, sample_rate=sample_rate,
+                            learning_rate=learning_rate, lr_decay=lr_decay, lr_decay_interval=lr_decay_interval,
+                            log_audio=log_audio)
+        self.learning_rate = learning_rate
+        self.lr_decay = lr_decay
+        self.lr_decay_interval = lr_decay_interval
+        self.control_hop = control_hop
+        self.log_audio = log_audio
+        self.sample_rate = sample_rate
+
+        # construction order == the reference's, so a seeded construction yields the same weights
+        self.embedding = ControlModule()
+        self.osc = HarmonicOscillator()
+        self.harmonic_mixer = nn.Conv1d(self.osc.n_harmonics, n_waveshapers, 1)
+        self.newt = NEWT()
+        with gin.config_scope("noise_synth"):
+            self.h_generator = TimeDistributedMLP()
+            self.noise_synth = FIRNoiseSynth()
+        self.reverb = Reverb()
+
+        object.__setattr__(self, "_engines", {})
+        object.__setattr__(self, "_loaded", {})
+        if control_hop != 128 or n_waveshapers != 64 or int(sample_rate) != 16000:
+            raise NotImplementedError("the CUDA path is built for gin/models/newt.gin "
+                                      "(control_hop 128, 64 waveshapers, 16 kHz)")
+
+    # ------------------------------------------------------------------ engine management
+    def _mlp_index(self, module) -> int:
+        if module is self.newt.mlp:
+            return 0
+        if module is self.h_generator:
+            return 1
+        raise NotImplementedError("this TimeDistributedMLP is not part of the model")
+
+    def _state_for_engine(self):
+        sd = {}
+        for k, v in self.state_dict(keep_vars=True).items():
+            sd[k] = v
+        # a FastNEWT keeps the source shaper weights out of reach (its method shadows the sub-module)
+        if isinstance(self.newt, FastNEWT):
+            for k, v in self.newt._modules["shaping_fn"].state_dict(keep_vars=True).items():
+                sd["newt.shaping_fn." + k] = v
+        return sd
+
+    def _engine_for(self, like: torch.Tensor) -> NwsEngine:
+        dev = like.device
+        if dev.type != "cuda":
+            raise RuntimeError("NeuralWaveshaping (B200) runs on CUDA only: inputs are on %s. There is no CPU "
+                               "fallback; move the model and inputs with .to('cuda')." % dev)
+        for m in self.modules():
+            if isinstance(m, BoundToRoot) and (m._nws_root_ref is None or m._nws_root_ref() is not self):
+                m._bind_root(self)
+        eng = self._engines.get(dev)
+        if eng is None:
+            eng = NwsEngine(dev)
+            self._engines[dev] = eng
+        sd = self._state_for_engine()
+        sig = tuple((sd[k].data_ptr(), sd[k]._version) for k in _lib.TENSOR_KEYS)
+        tag = self._loaded.get(dev)
+        if tag is None or tag[0] != sig:
+            eng.load_weights(sd)
+            tag = (sig, None)
+        if isinstance(self.newt, FastNEWT):
+            t = self.newt.lookup_table
+            lsig = (t.data_ptr(), t._version, self.newt.table_min, self.newt.table_max)
+            if tag[1] != lsig:
+                eng.set_lut(t, self.newt.table_min, self.newt.table_max)
+                tag = (tag[0], lsig)
+        self._loaded[dev] = tag
+        return eng
+
+    # ------------------------------------------------------------------ reference API
+    def render_exciter(self, f0):
+        raise NotImplementedError("the exciter exists only inside the fused audio-rate kernel; "
+                                  "see NwsEngine.audio(..., want_exciter=True) for a debugging tap")
+
+    def get_embedding(self, control):
+        return self.embedding(control)
+
+    def forward(self, f0, control, phase_shift=None, noise=None):
+        """f0 [B,1,T] Hz, control [B,C>=2,T] (channels 0,1 used) -> audio [B, T*control_hop].
+
+        `phase_shift` ([101], the uniform draw of the oscillator's random phase, i.e. torch.rand_like
+        (rand_phase)) and `noise` ([128*T-1] uniform) are optional test hooks replacing the two RNG
+        draws of the reference forward; by default both come from an on-device Philox stream seeded from
+        torch.initial_seed()."""
+        if not isinstance(f0, torch.Tensor) or not isinstance(control, torch.Tensor):
+            raise TypeError("f0 and control must be tensors")
+        eng = self._engine_for(f0)
+        return eng.forward(f0, control, u_phase=phase_shift, noise=noise, use_lut=isinstance(self.newt, FastNEWT))
+
+    def synthesise_from_host(self, f0, control, out=None, phase_shift=None, noise=None):
+        """Host tensors in, host tensor out through nws_forward_host (H2D, forward, D2H, sync)."""
+        dev = next(self.parameters()).device
+        eng = self._engine_for(torch.empty(0, device=dev))
+        B, _, T = f0.shape
+        if out is None:
+            out = torch.empty(B, T * self.control_hop, dtype=torch.float32, pin_memory=True)
+        return eng.forward_host(f0.contiguous(), control.contiguous(), out, phase_shift, noise,
+                                use_lut=isinstance(self.newt, FastNEWT))
+
+    # ------------------------------------------------------------------ Lightning-compatible loading
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
+        """Reads a PyTorch-Lightning checkpoint written by the reference's training script
+        (`state_dict` + `hyper_parameters`), without needing pytorch_lightning."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False,
+                          pickle_module=_PermissivePickle)
+        hp = dict(ckpt.get("hyper_parameters", {}) or {})
+        hp.update(kwargs)
+        names = ("n_waveshapers", "control_hop", "sample_rate", "learning_rate", "lr_decay", "lr_decay_interval",
+                 "log_audio")
+        model = cls(**{k: hp[k] for k in names if k in hp})
+        model.load_state_dict(ckpt["state_dict"], strict=strict)
+        return model
+
+    def save_hyperparameters(self, *args, **kwargs):
+        pass
+
+    def log(self, *args, **kwargs):
+        pass
+
+    def configure_optimizers(self):
+        raise NotImplementedError("training is outside the scope of the B200 forward path")
+
+    def training_step(self, batch, batch_idx):
+        raise NotImplementedError("training is outside the scope of the B200 forward path")
+
+    validation_step = training_step
+    test_step = training_step

@@ -1,0 +1,261 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via NwsEngine / the drop-in module) against
+the oracle (oracle/nws_oracle.py, pinned to the reference) and the committed golden vectors.
+
+Stated tolerances (fp32 path):
+  * random-init weights, U[0,1) inputs (the reference's timing inputs): max-abs <= 1e-5
+  * trained checkpoints, realistic f0: max-abs <= 1e-4 and RMS <= 1e-5
+    (the reference's own fp32-vs-fp64 spread there is 2.9e-4 / 3.7e-5)
+  * FastNEWT table indices and interpolation: bit-exact on identical shaper inputs
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nws_oracle as oracle
+from tests.helpers import err, golden_path, load_case, load_weights
+
+pytestmark = pytest.mark.gpu
+
+TOL_RAND = 1e-5
+TOL_CKPT_MAX, TOL_CKPT_RMS = 1e-4, 1e-5
+
+
+def _engine(tag):
+    from neural_waveshaping_synthesis_b200.engine import NwsEngine
+    w = load_weights(tag)
+    eng = NwsEngine("cuda:0")
+    eng.load_weights({k: v for k, v in w.items() if not k.startswith("data_")})
+    return eng, w
+
+
+@pytest.fixture(scope="module")
+def eng_rand():
+    return _engine("randinit")
+
+
+@pytest.fixture(scope="module")
+def eng_vn():
+    return _engine("vn")
+
+
+def _tols(tag):
+    return (TOL_RAND, TOL_RAND) if tag == "randinit" else (TOL_CKPT_MAX, TOL_CKPT_RMS)
+
+
+# ------------------------------------------------------------------------------ stage-level parity
+@pytest.mark.parametrize("tag", ["randinit", "vn"])
+def test_control_embedding(tag, eng_rand, eng_vn):
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    c = load_case("small_%s_newt" % tag)
+    emb = eng.control_embedding(c["control"].cuda())
+    e = err(emb, c["part_emb"])
+    # recurrent rounding is amplified on the trained violin weights (3.4e-4 between two
+    # correct fp32 GRU orders); what matters downstream is the audio error, checked in the full-path tests
+    assert e[0] < (2e-5 if tag == "randinit" else 1e-3), e
+    lit = oracle.gru_literal(w, c["control"])
+    lit = torch.nn.functional.conv1d(lit.transpose(1, 2), w["embedding.proj.weight"], w["embedding.proj.bias"])
+    assert err(emb, lit)[0] < (2e-5 if tag == "randinit" else 1e-3)
+
+
+@pytest.mark.parametrize("tag", ["randinit", "vn"])
+def test_td_mlps(tag, eng_rand, eng_vn):
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    c = load_case("small_%s_newt" % tag)
+    emb = c["part_emb"].cuda()
+    film = eng.td_mlp(0, emb)
+    H = eng.td_mlp(1, emb)
+    assert film.shape == c["part_film"].shape and H.shape == c["part_H"].shape
+    assert err(film, c["part_film"])[0] < 2e-5 * max(1.0, float(c["part_film"].abs().max()))
+    assert err(H, c["part_H"])[0] < 2e-5 * max(1.0, float(c["part_H"].abs().max()))
+
+
+@pytest.mark.parametrize("tag", ["randinit", "vn"])
+def test_exciter_and_newt(tag, eng_rand, eng_vn):
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    c = load_case("small_%s_newt" % tag)
+    out, exc = eng.audio(c["f0"].cuda(), c["part_film"].cuda(), c["u_phase"].cuda(), use_lut=False, want_exciter=True)
+    e = err(exc, c["part_exciter"])
+    assert e[0] < 2e-5, e
+    e = err(out, c["part_newt_out"][:, 0])
+    assert e[0] < _tols(tag)[0], e
+
+
+@pytest.mark.parametrize("tag", ["randinit", "vn"])
+def test_fastnewt_stage(tag, eng_rand, eng_vn):
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    c = load_case("small_%s_fast" % tag)
+    eng.set_lut(oracle.build_lookup_table(w))
+    out = eng.audio(c["f0"].cuda(), c["part_film"].cuda(), c["u_phase"].cuda(), use_lut=True)
+    e = err(out, c["part_newt_out"][:, 0])
+    assert e[0] < _tols(tag)[0], e
+
+
+@pytest.mark.parametrize("tag", ["randinit", "vn"])
+def test_lut_index_path_bit_exact(tag, eng_rand, eng_vn):
+    """Identical shaper inputs -> identical table indices and identical interpolated values."""
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    lut = oracle.build_lookup_table(w)
+    eng.set_lut(lut)
+    c = load_case("small_%s_fast" % tag)
+    film = oracle.td_mlp(w, "newt.mlp", c["part_emb"])
+    film_up = oracle.upsample_linear(film, c["part_exciter"].shape[-1])
+    g_i, b_i, _, _ = torch.split(film_up, 64, 1)
+    x = g_i * c["part_exciter"] + b_i
+    gen = torch.Generator().manual_seed(3)
+    x = torch.cat([x, (torch.rand(1, 64, x.shape[-1], generator=gen) * 8 - 4)], 0)  # incl. out-of-range inputs
+    _, lower, _, _ = oracle.lut_indices(x)
+    ref = oracle.lut_shaping_fn(lut, x)
+    y, lo = eng.lut_lookup(x.cuda())
+    assert torch.equal(lo.cpu().long(), lower)
+    assert torch.equal(y.cpu(), ref)
+
+
+@pytest.mark.parametrize("tag", ["randinit", "vn"])
+def test_lut_builder(tag, eng_rand, eng_vn):
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    ref = oracle.build_lookup_table(w)
+    eng.build_lut(4096, -3.0, 3.0, sample_points=torch.linspace(-3.0, 3.0, 4096))
+    lut = eng.get_lut()
+    assert err(lut, ref)[0] < 2e-6
+    eng.build_lut(4096, -3.0, 3.0)  # grid computed on the device
+    assert err(eng.get_lut(), ref)[0] < 2e-5
+    from neural_waveshaping_synthesis_b200.engine import shaper_eval
+    from neural_waveshaping_synthesis_b200._lib import SHAPER_KEYS
+    t = shaper_eval([w[k] for k in SHAPER_KEYS], torch.linspace(-3.0, 3.0, 4096).cuda())
+    assert torch.equal(t, lut)
+
+
+@pytest.mark.parametrize("tag", ["randinit", "vn"])
+def test_noise_branch(tag, eng_rand, eng_vn):
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    c = load_case("small_%s_newt" % tag)
+    nz = eng.noise(c["part_H"].cuda(), c["noise"].cuda())
+    ref = c["part_noise_out"][:, 0]
+    e = err(nz, ref)
+    assert e[0] < 2e-5 * max(1.0, float(ref.abs().max())), (e, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("tag,N", [("randinit", 768), ("vn", 1280), ("vn", 4096), ("vn", 32000), ("vn", 33024), ("vn", 64000)])
+def test_reverb(tag, N, eng_rand, eng_vn):
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    gen = torch.Generator().manual_seed(N)
+    x = torch.randn(3, N, generator=gen) * 0.1
+    ref = oracle.reverb(w, x)
+    y = eng.reverb(x.cuda())
+    e = err(y, ref)
+    assert e[0] < 1e-5 * max(1.0, float(ref.abs().max())), (e, float(ref.abs().max()))
+    lit = oracle.reverb_literal(w["reverb.ir"].numpy(), x.numpy())
+    assert err(y, lit)[0] < 1e-5 * max(1.0, float(ref.abs().max()))
+
+
+# ------------------------------------------------------------------------------ full path vs golden
+def _model(tag, fast):
+    import gin
+    from neural_waveshaping_synthesis.models.neural_waveshaping import NeuralWaveshaping
+    from neural_waveshaping_synthesis.models.modules.shaping import FastNEWT
+    gin.clear_config()
+    gin.parse_config_file(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gin", "models", "newt.gin"))
+    w = load_weights(tag)
+    m = NeuralWaveshaping()
+    m.load_state_dict({k: v for k, v in w.items() if not k.startswith("data_")})
+    m.eval()
+    if fast:
+        m.newt = FastNEWT(m.newt)   # built before .to(device), like the reference scripts
+    return m.to("cuda:0"), w
+
+
+@pytest.mark.parametrize("case,tag,fast", [
+    ("kat_randinit_newt", "randinit", False), ("kat_randinit_fast", "randinit", True),
+    ("kat_vn_newt", "vn", False), ("kat_vn_fast", "vn", True),
+    ("kat_fl_newt", "fl", False), ("kat_fl_fast", "fl", True),
+    ("kat_tpt_newt", "tpt", False), ("kat_tpt_fast", "tpt", True),
+    ("small_randinit_newt", "randinit", False), ("small_randinit_fast", "randinit", True),
+    ("small_vn_newt", "vn", False), ("small_vn_fast", "vn", True),
+    ("min_randinit_newt", "randinit", False), ("min_randinit_fast", "randinit", True),
+])
+def test_forward_vs_reference_golden(case, tag, fast):
+    m, w = _model(tag, fast)
+    c = load_case(case)
+    with torch.no_grad():
+        y = m(c["f0"].cuda(), c["control"].cuda(), phase_shift=c["u_phase"].cuda(), noise=c["noise"].cuda())
+    assert y.shape == c["out"].shape and y.dtype == torch.float32 and y.is_contiguous()
+    e = err(y, c["out"])
+    tmax, trms = _tols(tag)
+    assert e[0] < tmax and e[1] < trms, (case, e)
+    if fast:  # the table built by the CUDA shaper kernel vs the reference's table
+        z = np.load(golden_path("lut_%s.npz" % tag)) if tag in ("randinit", "vn") else None
+        if z is not None:
+            assert np.abs(m.newt.lookup_table.detach().cpu().numpy()[:, ::16] - z["lut_sub"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("bs", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768])
+def test_buffer_sweep_vs_golden(bs):
+    z = np.load(golden_path("sweep_randinit.npz"))
+    f0 = torch.from_numpy(z["bs%d_f0" % bs]).cuda()
+    control = torch.from_numpy(z["bs%d_control" % bs]).cuda()
+    u, noise = oracle.draw_rng(bs // 128, int(z["bs%d_rng_seed" % bs]))
+    for fast, key in ((False, "out"), (True, "out_fast")):
+        m, _ = _model("randinit", fast)
+        with torch.no_grad():
+            y = m(f0, control, phase_shift=u.reshape(-1).cuda(), noise=noise.cuda())
+        e = err(y, z["bs%d_%s" % (bs, key)])
+        assert e[0] < TOL_RAND, (bs, fast, e)
+
+
+# ------------------------------------------------------------------------------ full-size properties
+def test_full_size_batch_properties():
+    """BASELINE config sizes (B=64 x 4 s): every utterance is independent (neural_waveshaping.py:74-90
+    has no cross-batch op), the forward is deterministic given the draws, and a batch row equals the
+    same utterance run alone — checked bit-for-bit."""
+    m, w = _model("vn", True)
+    f0, control = oracle.realistic_inputs(500, w["data_mean"].numpy(), w["data_std"].numpy(), B=1)
+    gen = torch.Generator().manual_seed(5)
+    f0b = (f0 * (0.5 + torch.rand(64, 1, 1, generator=gen))).contiguous()
+    cb = (control + 0.1 * torch.randn(64, 2, 1, generator=gen)).contiguous()
+    u, noise = oracle.draw_rng(500, 7)
+    args = dict(phase_shift=u.reshape(-1).cuda(), noise=noise.cuda())
+    with torch.no_grad():
+        y1 = m(f0b.cuda(), cb.cuda(), **args)
+        y2 = m(f0b.cuda(), cb.cuda(), **args)
+        assert torch.equal(y1, y2)
+        assert torch.isfinite(y1).all()
+        for i in (0, 17, 63):
+            yi = m(f0b[i:i + 1].cuda(), cb[i:i + 1].cuda(), **args)
+            assert torch.equal(yi[0], y1[i]), i
+        ref = oracle.forward(w, f0b[63:64], cb[63:64], u, noise, lut=oracle.build_lookup_table(w))
+    e = err(y1[63:64], ref)
+    assert e[0] < TOL_CKPT_MAX and e[1] < TOL_CKPT_RMS, e
+
+
+def test_device_rng_path_and_errors():
+    m, w = _model("randinit", False)
+    f0 = torch.rand(2, 1, 16).cuda()
+    control = torch.rand(2, 2, 16).cuda()
+    with torch.no_grad():
+        torch.manual_seed(123)
+        a = m(f0, control)
+        torch.manual_seed(123)
+        b = m(f0, control)
+        c = m(f0, control)
+    assert a.shape == (2, 2048) and torch.isfinite(a).all()
+    assert torch.equal(a, b)            # same seed -> same Philox stream
+    assert not torch.equal(b, c)        # the stream advances between forwards
+    with pytest.raises(ValueError):
+        m(f0[:, :, :1], control[:, :, :1])          # T = 1: the reference raises too (stft reflect pad)
+    with pytest.raises(RuntimeError):
+        m(f0.cpu(), control.cpu())                   # no CPU fallback
+    with pytest.raises(ValueError):
+        m(f0.double(), control.double())
+    with pytest.raises(ValueError):
+        m(f0, control[:1])
+
+
+def test_host_buffer_entry_point():
+    m, w = _model("randinit", True)
+    c = load_case("small_randinit_fast")
+    out = torch.empty(c["out"].shape, dtype=torch.float32).pin_memory()
+    y = m.synthesise_from_host(c["f0"].contiguous(), c["control"].contiguous(), out=out,
+                               phase_shift=c["u_phase"].contiguous(), noise=c["noise"].contiguous())
+    assert err(y, c["out"])[0] < TOL_RAND
