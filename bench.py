@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the NWS forward hot path (BASELINE.json metric: audio samples/sec at 16 kHz).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--variant fastnewt|newt] [--batch-per-gpu B] [--seconds S]
+
+A step = one NeuralWaveshaping.forward over one batch of synthetic control streams.  N=1 workload
+(default): BASELINE.json configs[1] — FastNEWT LUT path, batch 64 x 4 s @ 16 kHz, inputs
+torch.rand like scripts/time_forward_pass.py:27-40, random-init weights of newt.gin
+(torch.manual_seed(0)); `--variant newt` gives configs[2].  N>1: the same batch per GPU (weak
+scaling), one process per GPU under torchrun, no collective on the data path, one NCCL
+all-reduce/all-gather of (seconds, samples) at the end.
+
+One JSON line on stdout (rank 0).  `value` is device-timed (CUDA events around each step on the
+launch stream, inputs resident in HBM, L2 flushed between steps); `e2e` is the same forward through
+the public module API from pinned host tensors with the H2D/D2H copies inside the timed region;
+`roofline` times the dominant kernel (nws_audio_fused_kernel) with the library's own stage events;
+`cpu_baseline` / `--impl reference` time the oracle port (the reference's op sequence on torch CPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+SR, HOP = 16000, 128
+ALGO_BYTES_PER_UTT_FRAME = 4 + 8 + 512   # f0 (1 fp32) + control (2 fp32) read, 128 fp32 samples written per frame
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="fastnewt", choices=["fastnewt", "newt"])
+    ap.add_argument("--batch-per-gpu", type=int, default=64)
+    ap.add_argument("--seconds", type=float, default=4.0)
+    ap.add_argument("--cpu-batch", type=int, default=8, help="utterances per CPU-reference step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clock and throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_weights():
+    """gin-configured random-init weights, torch.manual_seed(0)."""
+    import gin
+    import torch
+    from neural_waveshaping_synthesis.models.neural_waveshaping import NeuralWaveshaping
+    gin.clear_config()
+    gin.parse_config_file(os.path.join(REPO, "gin", "models", "newt.gin"))
+    torch.manual_seed(0)
+    return NeuralWaveshaping().eval()
+
+
+def cpu_reference_throughput(model, variant: str, T: int, batch: int, steps: int, warmup: int):
+    """Times the oracle port (reference op sequence, torch CPU, all host threads).  Returns
+    (samples_per_s, ms_per_step, threads)."""
+    import torch
+    from oracle import nws_oracle as oracle
+    w = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    lut = oracle.build_lookup_table(w) if variant == "fastnewt" else None
+    torch.manual_seed(1)
+    f0 = torch.rand(batch, 1, T)
+    control = torch.rand(batch, 2, T)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        u, noise = oracle.draw_rng(T)
+        oracle.forward(w, f0, control, u, noise, lut=lut, faithful_loop=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return batch * T * HOP / mean, mean * 1e3, torch.get_num_threads()
+
+
+def best_cpu_baseline(cpu_model, args, T):
+    """The reference's CPU path on this box: torch's intra-op thread count matters a lot for these small
+    ops (all cores is far from the best on a 100+ core host), so a few counts are tried and the best
+    throughput is reported — the comparison is against the reference at its best."""
+    import torch
+    ncpu = os.cpu_count() or 1
+    tried = []
+    for threads in sorted({min(ncpu, t) for t in (8, 16, 32, ncpu)}):
+        torch.set_num_threads(threads)
+        for batch, iters in ((1, 3), (args.cpu_batch, 2)):
+            sps, _, _ = cpu_reference_throughput(cpu_model, args.variant, T, batch, iters, 1)
+            tried.append((sps, threads, batch))
+    sps, threads, batch = max(tried)
+    return {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": "oracle port (reference op sequence incl. the faithful _lookup loop, torch CPU), %g s utterances; "
+                      "best of threads x batch: %s -> %d threads, batch %d" %
+                      (args.seconds, ", ".join("%dt/B%d: %.3g" % (t, b, v) for v, t, b in tried), threads, batch)}
+
+
+def run_reference(args):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    import torch
+    T = int(SR * args.seconds) // HOP
+    model = build_weights()
+    # pick the intra-op thread count at which the reference's CPU path runs fastest on this host
+    best = None
+    for threads in sorted({min(os.cpu_count() or 1, t) for t in (8, 16, 32, os.cpu_count() or 1)}):
+        torch.set_num_threads(threads)
+        probe, _, _ = cpu_reference_throughput(model, args.variant, T, args.cpu_batch, 1, 1)
+        if best is None or probe > best[0]:
+            best = (probe, threads)
+    torch.set_num_threads(best[1])
+    sps, ms, threads = cpu_reference_throughput(model, args.variant, T, args.cpu_batch, args.steps, args.warmup)
+    sample = ("oracle port of NeuralWaveshaping.forward (%s, faithful _lookup loop), %d of the %d utterances per step, "
+              "%g s each, torch CPU %d threads" % (args.variant, args.cpu_batch, args.batch_per_gpu * args.gpus,
+                                                  args.seconds, threads))
+    line = {
+        "impl": "reference", "metric": "audio samples/sec", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "rtf_per_utterance": (ms / 1e3) / (args.cpu_batch * args.seconds),
+        "config": workload_config(args),
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "%s forward, batch %d x %g s @ 16 kHz per GPU (BASELINE.json configs[%d])" %
+            ("FastNEWT LUT" if args.variant == "fastnewt" else "NEWT MLP", args.batch_per_gpu, args.seconds,
+             1 if args.variant == "fastnewt" else 2),
+            "variant": args.variant, "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * args.gpus,
+            "seconds": args.seconds, "frames": int(SR * args.seconds) // HOP, "sample_rate": SR,
+            "inputs": "torch.rand f0/control as scripts/time_forward_pass.py:27-40; random-init newt.gin weights, seed 0",
+            "rng": "on-device Philox draws inside the timed region", "l2": "flushed between timed steps (256 MiB write)",
+            "parallelism": "dp%d (utterance shards, no data-path collective)" % args.gpus}
+
+
+def run_b200(args):
+    import torch
+    rank, local_rank, world = env_rank()
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    torch.cuda.set_device(dev)
+
+    from neural_waveshaping_synthesis.models.modules.shaping import FastNEWT
+    from neural_waveshaping_synthesis_b200 import _lib
+    import copy
+    cpu_model = build_weights()
+    model = copy.deepcopy(cpu_model)          # .to() moves a module in place: keep the CPU copy apart
+    if args.variant == "fastnewt":
+        model.newt = FastNEWT(model.newt)
+    model = model.to(dev)
+    B, T = args.batch_per_gpu, int(SR * args.seconds) // HOP
+    N = T * HOP
+    torch.manual_seed(1 + rank)
+    f0_host = torch.rand(B, 1, T).pin_memory()
+    control_host = torch.rand(B, 2, T).pin_memory()
+    f0, control = f0_host.to(dev), control_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _lib.load_library()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed_steps(k, fn, with_flush=True):
+        evs = []
+        for _ in range(k):
+            if with_flush:
+                flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        return [a.elapsed_time(b) for a, b in evs]
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model(f0, control)
+        barrier()
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        lib.nws_launch_count(1)
+        per_step = timed_steps(args.steps, lambda: model(f0, control))
+        launches = int(lib.nws_launch_count(0))
+        barrier()
+        clocks = sampler.stop()
+        step_ms = sum(per_step) / len(per_step)
+
+        # ---- dominant-kernel time (library stage events) on the same workload
+        eng = model._engine_for(f0)
+        eng.set_profiling(True)
+        stage_acc = {}
+        for _ in range(args.steps):
+            flush.fill_(1)
+            model(f0, control)
+            for k, v in eng.stage_times_ms().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v / args.steps
+        eng.set_profiling(False)
+
+        # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of the audio
+        out_host = torch.empty(B, N, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            y = model(f0_host.to(dev, non_blocking=True), control_host.to(dev, non_blocking=True))
+            out_host.copy_(y, non_blocking=True)
+
+        for _ in range(args.warmup):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        e2e_s = (time.perf_counter() - t0) / args.steps
+
+    # ---- aggregate over ranks: time = max over ranks, samples = sum
+    from neural_waveshaping_synthesis_b200.sharding import aggregate_throughput
+    step_ms_max, total_samples = aggregate_throughput(step_ms, float(B * N), dev)
+    e2e_ms_max, _ = aggregate_throughput(e2e_s * 1e3, float(B * N), dev)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    audio_ms = stage_acc.get("audio_fused", 0.0)
+    algo_bytes = B * T * ALGO_BYTES_PER_UTT_FRAME          # 262,000 B per 4 s utterance
+    achieved = algo_bytes / (audio_ms * 1e-3) / 1e9 if audio_ms > 0 else None
+    # fp32-issue view of the same kernel: FMA-class lane-ops per sample over the 128 lanes/clk/SM
+    ops_per_sample = 8.0e3 if args.variant == "fastnewt" else 17.0e3
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    fma_peak = 148 * 128 * sm_mhz * 1e6
+    line = {
+        "metric": "audio samples/sec", "value": total_samples / (step_ms_max * 1e-3), "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "rtf_per_utterance": (step_ms_max * 1e-3) / (B * args.seconds),
+        "rtf_batch": (step_ms_max * 1e-3) / args.seconds,
+        "config": workload_config(args),
+        "e2e": {"value": total_samples / (e2e_ms_max * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms_max,
+                "h2d_bytes_per_step": B * 3 * T * 4, "d2h_bytes_per_step": B * N * 4},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "nws_audio_fused_kernel<%s>" % ("LUT" if args.variant == "fastnewt" else "MLP"),
+                     "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": audio_ms,
+                     "kernel_share_of_step": audio_ms / sum(stage_acc.values()) if stage_acc else None,
+                     "fp32_issue": {"lane_ops_per_sample": ops_per_sample,
+                                    "achieved_frac_of_fma_issue": (ops_per_sample * B * N / (audio_ms * 1e-3)) / fma_peak
+                                    if audio_ms > 0 else None,
+                                    "note": "the fused kernel is fp32-issue bound, not HBM bound (SURVEY.md §8(d))"}},
+        "stages_ms": stage_acc,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = best_cpu_baseline(cpu_model, args, T)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,79 @@
+// Self-test of the tcgen05 plumbing in nws_tc.cuh: D[128 x 64] = A[128 x K] . B[64 x K]^T with the
+// 3xTF32 split, operands written by threads in the canonical no-swizzle K-major layout, accumulator
+// in TMEM.  Exposed through the C ABI so tests/test_gpu_parity.py can check it against fp64.
+#include "nws_internal.cuh"
+#include "nws_tc.cuh"
+
+__global__ void __launch_bounds__(128) nws_selftest_umma_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                float* __restrict__ D, int K, int swap, int* status) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t a_bytes = 128 * K * 4, b_bytes = 64 * K * 4;
+  unsigned char* a_hi = smem_raw;
+  unsigned char* a_lo = a_hi + a_bytes;
+  unsigned char* b_hi = a_lo + a_bytes;
+  unsigned char* b_lo = b_hi + b_bytes;
+
+  for (int k = 0; k < K; ++k) {
+    const float a = A[tid * K + k], h = nws_tf32_hi(a);
+    *reinterpret_cast<float*>(a_hi + nws_umma_offset(tid, k, 128)) = h;
+    *reinterpret_cast<float*>(a_lo + nws_umma_offset(tid, k, 128)) = nws_tf32_lo(a, h);
+    if (tid < 64) {
+      const float b = B[tid * K + k], hb = nws_tf32_hi(b);
+      *reinterpret_cast<float*>(b_hi + nws_umma_offset(tid, k, 64)) = hb;
+      *reinterpret_cast<float*>(b_lo + nws_umma_offset(tid, k, 64)) = nws_tf32_lo(b, hb);
+    }
+  }
+  if (warp == 0) nws_tmem_alloc(&tmem_base_s, 64);
+  if (tid == 0) {
+    nws_mbar_init(&bar, 1);
+    nws_fence_mbar_init();
+  }
+  nws_fence_proxy_async();
+  nws_tc_fence_before();
+  __syncthreads();
+  nws_tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    const uint32_t idesc = nws_umma_idesc_tf32(128, 64);
+    const uint32_t lbo_a = 16 * 128, lbo_b = 8 * 128, sbo = 128;
+    for (int ks = 0; ks < K / 8; ++ks) {
+      const uint32_t oa = ks * 2 * lbo_a, ob = ks * 2 * lbo_b;
+      const uint64_t dah = swap ? nws_umma_smem_desc(nws_smem_u32(a_hi) + oa, sbo, lbo_a) : nws_umma_smem_desc(nws_smem_u32(a_hi) + oa, lbo_a, sbo);
+      const uint64_t dal = swap ? nws_umma_smem_desc(nws_smem_u32(a_lo) + oa, sbo, lbo_a) : nws_umma_smem_desc(nws_smem_u32(a_lo) + oa, lbo_a, sbo);
+      const uint64_t dbh = swap ? nws_umma_smem_desc(nws_smem_u32(b_hi) + ob, sbo, lbo_b) : nws_umma_smem_desc(nws_smem_u32(b_hi) + ob, lbo_b, sbo);
+      const uint64_t dbl = swap ? nws_umma_smem_desc(nws_smem_u32(b_lo) + ob, sbo, lbo_b) : nws_umma_smem_desc(nws_smem_u32(b_lo) + ob, lbo_b, sbo);
+      nws_umma_tf32(tmem, dah, dbh, idesc, ks > 0 ? 1u : 0u);
+      nws_umma_tf32(tmem, dal, dbh, idesc, 1u);
+      nws_umma_tf32(tmem, dah, dbl, idesc, 1u);
+    }
+    nws_umma_commit(&bar);
+  }
+  const bool ok = nws_mbar_wait(&bar, 0, 1u << 22);
+  nws_tc_fence_after();
+  if (ok) {
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      float v[16];
+      nws_tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) D[tid * 64 + c0 + i] = v[i];
+    }
+  }
+  if (tid == 0) status[0] = ok ? 1 : -1;
+  nws_tc_fence_before();
+  __syncthreads();
+  if (warp == 0) nws_tmem_dealloc(tmem, 64);
+}
+
+extern "C" int nws_selftest_umma(const float* A, const float* B, float* D, int K, int swap, int* status, void* stream) {
+  if (!A || !B || !D || !status || K < 8 || K > 104 || (K & 7)) { nws_set_error("nws_selftest_umma: bad argument"); return NWS_ERR_INVALID; }
+  const size_t smem = (size_t)(128 + 64) * K * 4 * 2;
+  NWS_CUDA_OK(cudaFuncSetAttribute(nws_selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nws_selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, swap, status);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}

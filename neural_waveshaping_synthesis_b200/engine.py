@@ -43,8 +43,6 @@ class NwsEngine:
         self.handle = handle
         self._ws: Optional[torch.Tensor] = None
         self._keep = None          # tensors whose pointers the last load call used
-        self._seed = None
-        self._offset = 0
         self.has_lut = False
         self.lut_shape = None
 
@@ -73,12 +71,13 @@ class NwsEngine:
         return self._workspace(n)
 
     def _next_rng(self, n_noise: int):
-        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-        if seed != self._seed:
-            self._seed, self._offset = seed, 0
-        off = self._offset
-        self._offset += (n_noise + 3) // 4 + 32
-        return seed, off
+        """(seed, offset) of this forward's Philox draws, reserved on torch's CUDA generator exactly as
+        torch's own CUDA kernels reserve theirs — so torch.manual_seed(s) makes the forward reproducible
+        and consecutive forwards consume consecutive parts of the stream."""
+        gen = torch.cuda.default_generators[self.device.index]
+        off = gen.get_offset()
+        gen.set_offset(off + 4 * ((n_noise + 3) // 4 + 32))
+        return gen.initial_seed() & 0xFFFFFFFFFFFFFFFF, off // 4
 
     # ------------------------------------------------------------------ weights / LUT
     def load_weights(self, state: Dict[str, torch.Tensor]):

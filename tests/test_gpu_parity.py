@@ -208,7 +208,7 @@ def test_buffer_sweep_vs_golden(bs):
 def test_full_size_batch_properties():
     """BASELINE config sizes (B=64 x 4 s): every utterance is independent (neural_waveshaping.py:74-90
     has no cross-batch op), the forward is deterministic given the draws, and a batch row equals the
-    same utterance run alone — checked bit-for-bit."""
+    same utterance run alone (to fp32 round-off; repeat runs are bit-identical)."""
     m, w = _model("vn", True)
     f0, control = oracle.realistic_inputs(500, w["data_mean"].numpy(), w["data_std"].numpy(), B=1)
     gen = torch.Generator().manual_seed(5)
@@ -223,7 +223,9 @@ def test_full_size_batch_properties():
         assert torch.isfinite(y1).all()
         for i in (0, 17, 63):
             yi = m(f0b[i:i + 1].cuda(), cb[i:i + 1].cuda(), **args)
-            assert torch.equal(yi[0], y1[i]), i
+            # not bit-equal by design: the reverb transforms two utterances per complex FFT (real/imaginary
+            # parts), so the partner utterance perturbs the rounding — values agree to fp32 round-off
+            assert err(yi[0], y1[i])[0] < 2e-6 * float(y1[i].abs().max()), i
         ref = oracle.forward(w, f0b[63:64], cb[63:64], u, noise, lut=oracle.build_lookup_table(w))
     e = err(y1[63:64], ref)
     assert e[0] < TOL_CKPT_MAX and e[1] < TOL_CKPT_RMS, e
