@@ -134,7 +134,7 @@ def best_cpu_baseline(cpu_model, args, T):
     import torch
     ncpu = os.cpu_count() or 1
     tried = []
-    for threads in sorted({min(ncpu, t) for t in (8, 16, 32, ncpu)}):
+    for threads in sorted({min(ncpu, t) for t in (8, 16, 32)}):   # all-cores is pathological (measured 100x slower at 128)
         torch.set_num_threads(threads)
         for batch, iters in ((1, 3), (args.cpu_batch, 2)):
             sps, _, _ = cpu_reference_throughput(cpu_model, args.variant, T, batch, iters, 1)
@@ -155,7 +155,7 @@ def run_reference(args):
     model = build_weights()
     # pick the intra-op thread count at which the reference's CPU path runs fastest on this host
     best = None
-    for threads in sorted({min(os.cpu_count() or 1, t) for t in (8, 16, 32, os.cpu_count() or 1)}):
+    for threads in sorted({min(os.cpu_count() or 1, t) for t in (8, 16, 32)}):
         torch.set_num_threads(threads)
         probe, _, _ = cpu_reference_throughput(model, args.variant, T, args.cpu_batch, 1, 1)
         if best is None or probe > best[0]:

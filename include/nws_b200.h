@@ -181,6 +181,11 @@ int nws_set_profiling(NwsHandle handle, int enable);
 /* Waits for the recorded events and writes the last forward's stage times (ms) to ms_out[0..9]. */
 int nws_get_stage_times(NwsHandle handle, float* ms_out, int n);
 
+/* Implementation of the fused audio-rate kernel's harmonic mixer: 1 (default) = tcgen05 3xTF32 with
+ * the accumulator in TMEM (csrc/nws_audio_tc.cu), 0 = fp32 SIMT (csrc/nws_audio.cu, kept as the
+ * in-library cross-check). */
+int nws_set_audio_impl(NwsHandle handle, int impl);
+
 /* Self-test of the tcgen05 path (csrc/nws_tc.cuh): D[128,64] = A[128,K] . B[64,K]^T, 3xTF32 in TMEM,
  * K a multiple of 8 up to 104.  status[0] = 1 on completion, -1 if the MMA never signalled. */
 int nws_selftest_umma(const float* A, const float* B, float* D, int K, int swap_lbo_sbo, int* status, void* stream);

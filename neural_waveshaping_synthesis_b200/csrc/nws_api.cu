@@ -204,6 +204,19 @@ static int check_common(NwsContext* ctx, int B, int T, void* ws, size_t ws_bytes
     if ((ctx)->profile) { cudaEventRecord((ctx)->ev[2 * (st) + 1], (s)); (ctx)->ev_recorded[(st)] = true; } \
   } while (0)
 
+static int launch_audio(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
+                        const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
+                        int use_lut, cudaStream_t s) {
+  return ctx->audio_impl ? nws_launch_audio_tc(ctx, f0, carry, film, u_phase, noise_in, out, exciter_out, B, T, use_lut, s)
+                         : nws_launch_audio(ctx, f0, carry, film, u_phase, noise_in, out, exciter_out, B, T, use_lut, s);
+}
+
+extern "C" int nws_set_audio_impl(NwsHandle ctx, int impl) {
+  if (!ctx || (impl != 0 && impl != 1)) { nws_set_error("nws_set_audio_impl: impl must be 0 (fp32 SIMT mixer) or 1 (tcgen05 mixer)"); return NWS_ERR_INVALID; }
+  ctx->audio_impl = impl;
+  return NWS_OK;
+}
+
 extern "C" int nws_set_profiling(NwsHandle ctx, int enable) {
   if (!ctx) { nws_set_error("nws_set_profiling: NULL handle"); return NWS_ERR_INVALID; }
   if (enable && !ctx->ev[0]) {
@@ -252,7 +265,7 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   NWS_STAGE(ctx, kStNoiseSpec, s, nws_launch_noise_spectrum(ctx, noise, w.xspec, T, s));
   NWS_STAGE(ctx, kStNoiseFilter, s, nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, s));
   // fused audio-rate kernel: dry = newt(exciter) + noise
-  NWS_STAGE(ctx, kStAudio, s, nws_launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, use_lut, s));
+  NWS_STAGE(ctx, kStAudio, s, launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, use_lut, s));
   // reverb
   NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb(ctx, w.dry, out, w.rev, B, N, s));
   return NWS_OK;
@@ -329,7 +342,7 @@ extern "C" int nws_stage_audio(NwsHandle ctx, const float* f0, const float* film
   cudaStream_t s = (cudaStream_t)stream;
   NWS_TRY(nws_launch_bct_to_rows(film, w.film, B, kFilm, T, kFilm, s));
   NWS_TRY(nws_launch_phase_carry(f0, w.carry, B, T, s));
-  return nws_launch_audio(ctx, f0, w.carry, w.film, u_phase, nullptr, newt_out, exciter_out, B, T, use_lut, s);
+  return launch_audio(ctx, f0, w.carry, w.film, u_phase, nullptr, newt_out, exciter_out, B, T, use_lut, s);
 }
 
 extern "C" int nws_stage_noise(NwsHandle ctx, const float* H, const float* noise, float* out, int B, int T,

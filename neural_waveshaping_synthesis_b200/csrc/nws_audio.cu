@@ -8,6 +8,7 @@
 // utterance, persistent CTAs striding over the B*T hop tiles.  Harmonic-mixer rows, phase shifts
 // and shaper weights stay resident in shared memory for the CTA's lifetime; nothing audio-rate
 // except the final sample is written to HBM (the reference materialises ~34 KB per sample).
+#include "nws_audio_common.cuh"
 #include "nws_internal.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -55,6 +56,15 @@ __global__ void nws_pack_kernel(NwsPackArgs a, NwsPackedLayout L, float* __restr
   else if (in(L.proj_b, kEmb)) v = a.t[NWS_T_PROJ_B][i - L.proj_b];
   else if (in(L.hmix_wt, kHarmPad * kShapers)) { const int j = i - L.hmix_wt, k = j / kShapers, c = j % kShapers; v = k < kHarm ? a.t[NWS_T_HMIX_W][c * kHarm + k] : 0.f; }
   else if (in(L.hmix_b, kShapers)) v = a.t[NWS_T_HMIX_B][i - L.hmix_b];
+  else if (in(L.hmix_umma, 2 * kHarmPad * kShapers)) {
+    // canonical no-swizzle K-major layout of the [64 x 104] B operand (see nws_tc.cuh): float index q ->
+    // chunk (4 k's) = q / 256, 8-row group = (q % 256) / 32, row in group = (q % 32) / 4, k in chunk = q % 4
+    const int j = i - L.hmix_umma, part = j / (kHarmPad * kShapers), q = j % (kHarmPad * kShapers);
+    const int k = (q / 256) * 4 + (q & 3), c = ((q % 256) / 32) * 8 + ((q & 31) >> 2);
+    const float w = k < kHarm ? a.t[NWS_T_HMIX_W][c * kHarm + k] : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    v = part == 0 ? hi : __uint_as_float(__float_as_uint(w - hi) & 0xffffe000u);
+  }
   else if (in(L.mix_w, kShapers)) v = a.t[NWS_T_MIX_W][i - L.mix_w];
   else if (in(L.mix_b, 1)) v = a.t[NWS_T_MIX_B][0];
   else if (in(L.rand_phase, kHarmPad)) { const int k = i - L.rand_phase; v = k < kHarm ? a.t[NWS_T_OSC_RAND_PHASE][k] : 0.f; }
@@ -96,44 +106,6 @@ int nws_launch_pack_weights(NwsContext* ctx, const float* const* tensors, cudaSt
   return NWS_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// One shaper's sine-MLP (TrainableNonlinearity.forward, shaping.py:36-37 with Sine, depth 4, width 8):
-// y = sin(w4 . sin(W3 sin(W2 sin(w1*(s*x) + b1) + b2) + b3) + b4).  `wp` = packed record (kShp* offsets).
-__device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, float x) {
-  const float4 hd = *reinterpret_cast<const float4*>(wp);
-  const float u = hd.x * x;
-  float h1[8], h2[8];
-  {
-    const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW1), wb = *reinterpret_cast<const float4*>(wp + kShpW1 + 4);
-    const float4 ba = *reinterpret_cast<const float4*>(wp + kShpB1), bb = *reinterpret_cast<const float4*>(wp + kShpB1 + 4);
-    h1[0] = nws_sinf(fmaf(wa.x, u, ba.x)); h1[1] = nws_sinf(fmaf(wa.y, u, ba.y));
-    h1[2] = nws_sinf(fmaf(wa.z, u, ba.z)); h1[3] = nws_sinf(fmaf(wa.w, u, ba.w));
-    h1[4] = nws_sinf(fmaf(wb.x, u, bb.x)); h1[5] = nws_sinf(fmaf(wb.y, u, bb.y));
-    h1[6] = nws_sinf(fmaf(wb.z, u, bb.z)); h1[7] = nws_sinf(fmaf(wb.w, u, bb.w));
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW2 + j * 8), wb = *reinterpret_cast<const float4*>(wp + kShpW2 + j * 8 + 4);
-    float a = wp[kShpB2 + j];
-    a = fmaf(wa.x, h1[0], a); a = fmaf(wa.y, h1[1], a); a = fmaf(wa.z, h1[2], a); a = fmaf(wa.w, h1[3], a);
-    a = fmaf(wb.x, h1[4], a); a = fmaf(wb.y, h1[5], a); a = fmaf(wb.z, h1[6], a); a = fmaf(wb.w, h1[7], a);
-    h2[j] = nws_sinf(a);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW3 + j * 8), wb = *reinterpret_cast<const float4*>(wp + kShpW3 + j * 8 + 4);
-    float a = wp[kShpB3 + j];
-    a = fmaf(wa.x, h2[0], a); a = fmaf(wa.y, h2[1], a); a = fmaf(wa.z, h2[2], a); a = fmaf(wa.w, h2[3], a);
-    a = fmaf(wb.x, h2[4], a); a = fmaf(wb.y, h2[5], a); a = fmaf(wb.z, h2[6], a); a = fmaf(wb.w, h2[7], a);
-    h1[j] = nws_sinf(a);
-  }
-  const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW4), wb = *reinterpret_cast<const float4*>(wp + kShpW4 + 4);
-  float a = hd.y;
-  a = fmaf(wa.x, h1[0], a); a = fmaf(wa.y, h1[1], a); a = fmaf(wa.z, h1[2], a); a = fmaf(wa.w, h1[3], a);
-  a = fmaf(wb.x, h1[4], a); a = fmaf(wb.y, h1[5], a); a = fmaf(wb.z, h1[6], a); a = fmaf(wb.w, h1[7], a);
-  return nws_sinf(a);
-}
-
 // FastNEWT._init_lookup_table (shaping.py:107-119): table[c][i] = shaper_c(linspace(min,max,size)[i]).
 __global__ void nws_build_lut_kernel(const float* __restrict__ shaper, const float* __restrict__ points,
                                      float* __restrict__ lut, int table_size, float tmin, float tmax) {
@@ -152,26 +124,6 @@ int nws_launch_build_lut(const NwsContext* ctx, const float* points, float* lut,
 }
 
 // ------------------------------------------------------------------------------------------------
-struct NwsAudioParams {
-  const float* f0;        // [B][T]
-  const double* carry;    // [B][T]
-  const float* film;      // [B*T][256] frame-major
-  const float* u_phase;   // [101]
-  const float* hmix_wt;   // [104][64]
-  const float* hmix_b;    // [64]
-  const float* rand_phase;// [104]
-  const float* shaper;    // [64][176]
-  const float* mix_w;     // [64]
-  const float* mix_b;     // [1]
-  const float* lut;       // [64][lut_size]
-  int lut_size;
-  float lut_min, lut_span, lut_span_rcp;
-  const float* noise_in;  // [B][N] or null: added to the mixdown (neural_waveshaping.py:85-86)
-  float* out;             // [B][N]
-  float* exciter_out;     // [B][64][N] or null
-  int B, T;
-};
-
 constexpr int kAudioThreads = 128;
 // shared memory (floats): hmix_wt | hmix_b | shift | mix_w | film[3][256] | e[64][128] | (MLP) shaper
 constexpr int kSmWt = 0;

@@ -1,0 +1,64 @@
+// Pieces shared by the two implementations of the fused audio-rate kernel (nws_audio.cu: fp32 SIMT
+// harmonic mixer; nws_audio_tc.cu: tcgen05 harmonic mixer).
+#pragma once
+#include "nws_internal.cuh"
+
+struct NwsAudioParams {
+  const float* f0;        // [B][T]
+  const double* carry;    // [B][T]
+  const float* film;      // [B*T][256] frame-major
+  const float* u_phase;   // [101]
+  const float* hmix_wt;   // [104][64]
+  const float* hmix_b;    // [64]
+  const float* rand_phase;// [104]
+  const float* shaper;    // [64][176]
+  const float* mix_w;     // [64]
+  const float* mix_b;     // [1]
+  const float* lut;       // [64][lut_size]
+  int lut_size;
+  float lut_min, lut_span, lut_span_rcp;
+  const float* noise_in;  // [B][N] or null: added to the mixdown (neural_waveshaping.py:85-86)
+  float* out;             // [B][N]
+  float* exciter_out;     // [B][64][N] or null
+  int B, T;
+};
+
+
+// ------------------------------------------------------------------------------------------------
+// One shaper's sine-MLP (TrainableNonlinearity.forward, shaping.py:36-37 with Sine, depth 4, width 8):
+// y = sin(w4 . sin(W3 sin(W2 sin(w1*(s*x) + b1) + b2) + b3) + b4).  `wp` = packed record (kShp* offsets).
+__device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, float x) {
+  const float4 hd = *reinterpret_cast<const float4*>(wp);
+  const float u = hd.x * x;
+  float h1[8], h2[8];
+  {
+    const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW1), wb = *reinterpret_cast<const float4*>(wp + kShpW1 + 4);
+    const float4 ba = *reinterpret_cast<const float4*>(wp + kShpB1), bb = *reinterpret_cast<const float4*>(wp + kShpB1 + 4);
+    h1[0] = nws_sinf(fmaf(wa.x, u, ba.x)); h1[1] = nws_sinf(fmaf(wa.y, u, ba.y));
+    h1[2] = nws_sinf(fmaf(wa.z, u, ba.z)); h1[3] = nws_sinf(fmaf(wa.w, u, ba.w));
+    h1[4] = nws_sinf(fmaf(wb.x, u, bb.x)); h1[5] = nws_sinf(fmaf(wb.y, u, bb.y));
+    h1[6] = nws_sinf(fmaf(wb.z, u, bb.z)); h1[7] = nws_sinf(fmaf(wb.w, u, bb.w));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW2 + j * 8), wb = *reinterpret_cast<const float4*>(wp + kShpW2 + j * 8 + 4);
+    float a = wp[kShpB2 + j];
+    a = fmaf(wa.x, h1[0], a); a = fmaf(wa.y, h1[1], a); a = fmaf(wa.z, h1[2], a); a = fmaf(wa.w, h1[3], a);
+    a = fmaf(wb.x, h1[4], a); a = fmaf(wb.y, h1[5], a); a = fmaf(wb.z, h1[6], a); a = fmaf(wb.w, h1[7], a);
+    h2[j] = nws_sinf(a);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW3 + j * 8), wb = *reinterpret_cast<const float4*>(wp + kShpW3 + j * 8 + 4);
+    float a = wp[kShpB3 + j];
+    a = fmaf(wa.x, h2[0], a); a = fmaf(wa.y, h2[1], a); a = fmaf(wa.z, h2[2], a); a = fmaf(wa.w, h2[3], a);
+    a = fmaf(wb.x, h2[4], a); a = fmaf(wb.y, h2[5], a); a = fmaf(wb.z, h2[6], a); a = fmaf(wb.w, h2[7], a);
+    h1[j] = nws_sinf(a);
+  }
+  const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW4), wb = *reinterpret_cast<const float4*>(wp + kShpW4 + 4);
+  float a = hd.y;
+  a = fmaf(wa.x, h1[0], a); a = fmaf(wa.y, h1[1], a); a = fmaf(wa.z, h1[2], a); a = fmaf(wa.w, h1[3], a);
+  a = fmaf(wb.x, h1[4], a); a = fmaf(wb.y, h1[5], a); a = fmaf(wb.z, h1[6], a); a = fmaf(wb.w, h1[7], a);
+  return nws_sinf(a);
+}
+

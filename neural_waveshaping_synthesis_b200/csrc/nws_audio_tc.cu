@@ -1,0 +1,267 @@
+// Fused audio-rate kernel, tensor-core version: the harmonic mixer (Conv1d 101->64 at audio rate,
+// neural_waveshaping.py:54,66 — 6,464 of the ~8,000 FMA per sample of the FastNEWT path) runs on the
+// 5th-gen tensor cores as a 3xTF32 GEMM with the accumulator in TMEM; everything else is as in
+// nws_audio.cu (same scalar recipes from nws_math.h).
+//
+// CTA = 4 warpgroups (512 threads), persistent, one CTA per SM.  A warpgroup owns one hop tile at a
+// time: thread = sample = TMEM lane.
+//   1. threads generate the oscillator bank sin(k*phase + shift_k)*mask_k for KS harmonics at a time,
+//      split each value into tf32 hi/lo parts and store them (STS.128, conflict-free) as the A operand
+//      in the canonical no-swizzle K-major UMMA layout — double-buffered stages;
+//   2. one elected thread issues tcgen05.mma kind::tf32 (M=128 samples, N=64 channels, K=8) three times
+//      per k-step (A_hi B_hi + A_lo B_hi + A_hi B_lo) against the mixer weights resident in shared
+//      memory, and commits to the stage's mbarrier — the tensor pipe works on stage s while the threads
+//      already compute the sines of stage s+1, and other warpgroups fill the gaps;
+//   3. when the last commit lands, each thread reads its own TMEM lane (its sample's 64 exciter
+//      channels) a few columns at a time and runs FiLM -> shaper (LUT or sine MLP) -> FiLM -> mixdown.
+// Nothing audio-rate is written to HBM except the final sample.
+#include "nws_audio_common.cuh"
+#include "nws_tc.cuh"
+
+namespace {
+
+constexpr int kWgs = 4;                  // warpgroups per CTA
+constexpr int kTcThreads = kWgs * 128;
+constexpr int kWBytes = kHarmPad * kShapers * 4;       // one tf32 part of the B operand (26,624 B)
+constexpr uint32_t kLboA = 16 * 128, kLboB = 8 * 128, kSbo = 128;
+
+template <bool USE_LUT>
+struct TcCfg {
+  static constexpr int KS = USE_LUT ? 16 : 8;                 // harmonics per A stage
+  static constexpr int NST = (kHarmPad + KS - 1) / KS;        // stages per tile (7 or 13)
+  static constexpr int kStageBytes = 128 * KS * 4;            // one tf32 part of one stage
+  static constexpr int kChPerLd = USE_LUT ? 4 : 2;            // exciter channels per TMEM load
+  // dynamic shared memory layout (bytes)
+  static constexpr int oW = 0;                                // W_hi | W_lo
+  static constexpr int oA = oW + 2 * kWBytes;                 // [wg][stage][hi|lo]
+  static constexpr int oFilm = oA + kWgs * 2 * 2 * kStageBytes;  // [wg][3][256] floats
+  static constexpr int oSmall = oFilm + kWgs * 3 * kFilm * 4;    // hmix_b[64] | shift[104] | mix_w[64] floats
+  static constexpr int oShaper = oSmall + (kShapers + kHarmPad + kShapers) * 4;
+  static constexpr int kBytes = oShaper + (USE_LUT ? 0 : kShapers * kShaperStride * 4);
+};
+
+__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld<2>(uint32_t taddr, float* v) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float* v) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+
+template <bool USE_LUT>
+__global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAudioParams p, const float* __restrict__ w_umma,
+                                                                     int* __restrict__ fault) {
+  using C = TcCfg<USE_LUT>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bars[kWgs][2];
+  __shared__ double warp_tot[kWgs][4];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, lane = tid & 31, wwarp = wt >> 5;
+  const int T = p.T, N = T * kHop;
+  float* sm_small = reinterpret_cast<float*>(smem + C::oSmall);
+  float* sm_hb = sm_small;
+  float* sm_shift = sm_small + kShapers;
+  float* sm_mixw = sm_shift + kHarmPad;
+  float* sm_film = reinterpret_cast<float*>(smem + C::oFilm) + wg * 3 * kFilm;
+  float* sm_shaper = reinterpret_cast<float*>(smem + C::oShaper);
+  unsigned char* a_base = smem + C::oA + wg * 4 * C::kStageBytes;   // [stage][hi|lo]
+
+  // ---- CTA-lifetime staging
+  for (int i = tid; i < 2 * kWBytes / 16; i += kTcThreads)
+    reinterpret_cast<float4*>(smem + C::oW)[i] = reinterpret_cast<const float4*>(w_umma)[i];
+  if (tid < kShapers) {
+    sm_hb[tid] = p.hmix_b[tid];
+    sm_mixw[tid] = p.mix_w[tid];
+  }
+  if (tid < kHarmPad) sm_shift[tid] = tid < kHarm ? nws_phase_shift(p.u_phase[tid], p.rand_phase[tid]) : 0.f;
+  if (!USE_LUT)
+    for (int i = tid; i < kShapers * kShaperStride / 4; i += kTcThreads)
+      reinterpret_cast<float4*>(sm_shaper)[i] = reinterpret_cast<const float4*>(p.shaper)[i];
+  if (tid < 32) nws_tmem_alloc(&tmem_base_s, 64 * kWgs);
+  if (tid == 0) {
+    for (int i = 0; i < kWgs * 2; ++i) nws_mbar_init(&bars[0][0] + i, 1);
+    nws_fence_mbar_init();
+  }
+  nws_fence_proxy_async();   // the weight tiles were written through the generic proxy
+  nws_tc_fence_before();
+  __syncthreads();
+  nws_tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_s + wg * 64;                       // this warpgroup's 64 columns
+  const uint32_t tmem_lane = tmem_acc + ((uint32_t)(wwarp * 32) << 16);   // this warp's lane quarter
+  const uint32_t idesc = nws_umma_idesc_tf32(128, 64);
+  const uint32_t w_hi_addr = nws_smem_u32(smem + C::oW), w_lo_addr = w_hi_addr + kWBytes;
+  const uint32_t a_addr = nws_smem_u32(a_base);
+  const float mix_b = p.mix_b[0];
+  const float inv_hop = (float)T / (float)N;
+  const long long n_tiles = (long long)p.B * T;
+  uint32_t uses0 = 0, uses1 = 0;   // completed-or-pending commits per stage buffer (same in every thread)
+  bool ok = true;
+
+  for (long long tile = (long long)blockIdx.x * kWgs + wg; tile < n_tiles; tile += (long long)gridDim.x * kWgs) {
+    const int b = (int)(tile / T), t = (int)(tile - (long long)b * T);
+    wg_barrier(wg);   // previous tile: film / warp_tot no longer read, TMEM loads done (fence below)
+    for (int i = wt; i < 3 * kFilm / 4; i += 128) {
+      const int slot = i / (kFilm / 4), fr = t - 1 + slot;
+      if (fr >= 0 && fr < T)
+        reinterpret_cast<float4*>(sm_film)[i] =
+            reinterpret_cast<const float4*>(p.film + ((size_t)b * T + fr) * kFilm)[i - slot * (kFilm / 4)];
+    }
+    // ---- f0 upsample and the cumsum of generators.py:59 (fp64 scan + per-hop carry)
+    const int n = t * kHop + wt;
+    const NwsLerp lc = nws_lerp_coords(n, T, inv_hop);
+    const float* f0b = p.f0 + (size_t)b * T;
+    const float f0u = nws_lerp_apply(lc, f0b[lc.i0], f0b[lc.i1]);
+    double v = (double)f0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) warp_tot[wg][wwarp] = v;
+    wg_barrier(wg);
+    double pre = p.carry[(size_t)b * T + t];
+    for (int w = 0; w < wwarp; ++w) pre += warp_tot[wg][w];
+    const float csum = (float)(pre + v);
+    const float phase = nws_phase_from_cumsum(csum, (float)kSampleRate);
+
+    // ---- oscillator bank -> A operand stages -> tcgen05.mma
+#pragma unroll 1
+    for (int st = 0; st < C::NST; ++st) {
+      const int buf = st & 1, k0 = st * C::KS;
+      const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;   // last stage may be short
+      const uint32_t prior = buf ? uses1 : uses0;
+      if (prior > 0 && ok) ok = nws_mbar_wait(&bars[wg][buf], (prior - 1) & 1);   // MMAs that read this buffer are done
+      unsigned char* hi = a_base + buf * 2 * C::kStageBytes;
+      unsigned char* lo = hi + C::kStageBytes;
+#pragma unroll
+      for (int kk = 0; kk < C::KS; kk += 4) {
+        if (kk < ks_here) {
+          float h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + kk + j + 1;   // harmonic number
+            float s = 0.f;
+            if (k <= kHarm) {
+              s = nws_sinf(nws_harmonic_arg(k, phase, sm_shift[k - 1]));
+              s = NWS_MUL(f0u, (float)k) < 0.5f * kSampleRate ? s : 0.f;
+            }
+            h[j] = nws_tf32_hi(s);
+            l[j] = nws_tf32_lo(s, h[j]);
+          }
+          const uint32_t off = (kk >> 2) * kLboA + wt * 16;   // chunk kk/4, row wt: conflict-free 16 B per thread
+          *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      nws_fence_proxy_async();
+      nws_tc_fence_before();
+      wg_barrier(wg);
+      if (wt == 0) {
+        nws_tc_fence_after();
+        const uint32_t a_hi = a_addr + buf * 2 * C::kStageBytes, a_lo = a_hi + C::kStageBytes;
+        for (int j = 0; j < ks_here / 8; ++j) {
+          const uint64_t dah = nws_umma_smem_desc(a_hi + j * 2 * kLboA, kLboA, kSbo);
+          const uint64_t dal = nws_umma_smem_desc(a_lo + j * 2 * kLboA, kLboA, kSbo);
+          const uint32_t wb = (k0 / 4 + 2 * j) * kLboB;
+          const uint64_t dbh = nws_umma_smem_desc(w_hi_addr + wb, kLboB, kSbo);
+          const uint64_t dbl = nws_umma_smem_desc(w_lo_addr + wb, kLboB, kSbo);
+          nws_umma_tf32(tmem_acc, dah, dbh, idesc, (st | j) ? 1u : 0u);
+          nws_umma_tf32(tmem_acc, dal, dbh, idesc, 1u);
+          nws_umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
+        }
+        nws_umma_commit(&bars[wg][buf]);
+      }
+      if (buf) ++uses1; else ++uses0;
+    }
+    {  // accumulator complete when the last stage's commit lands (a commit covers all earlier MMAs)
+      const int lb = (C::NST - 1) & 1;
+      const uint32_t u = lb ? uses1 : uses0;
+      if (ok) ok = nws_mbar_wait(&bars[wg][lb], (u - 1) & 1);
+      nws_tc_fence_after();
+    }
+
+    // ---- FiLM -> shaper -> FiLM -> mixdown (shaping.py:67-79), exciter read from this thread's TMEM lane
+    const float* fa = sm_film + (lc.i0 - (t - 1)) * kFilm;
+    const float* fb = sm_film + (lc.i1 - (t - 1)) * kFilm;
+    float mix = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kShapers; c0 += C::kChPerLd) {
+      float ev[C::kChPerLd];
+      tmem_ld<C::kChPerLd>(tmem_lane + c0, ev);
+#pragma unroll
+      for (int i = 0; i < C::kChPerLd; ++i) {
+        const int c = c0 + i;
+        const float e = ev[i] + sm_hb[c];
+        if (p.exciter_out) p.exciter_out[((size_t)b * kShapers + c) * N + n] = e;
+        const float g_i = nws_lerp_apply(lc, fa[c], fb[c]);
+        const float b_i = nws_lerp_apply(lc, fa[kShapers + c], fb[kShapers + c]);
+        const float g_n = nws_lerp_apply(lc, fa[2 * kShapers + c], fb[2 * kShapers + c]);
+        const float b_n = nws_lerp_apply(lc, fa[3 * kShapers + c], fb[3 * kShapers + c]);
+        const float x = NWS_ADD(NWS_MUL(g_i, e), b_i);
+        float y;
+        if (USE_LUT) {
+          const NwsLutIdx li = nws_lut_index(x, p.lut_size, p.lut_min, p.lut_span, p.lut_span_rcp);
+          const float* row = p.lut + (size_t)c * p.lut_size;
+          y = nws_lut_lerp(__ldg(row + li.lower), __ldg(row + li.upper), li.fract);
+        } else {
+          y = nws_shaper_mlp(sm_shaper + c * kShaperStride, x);
+        }
+        const float z = NWS_ADD(NWS_MUL(g_n, y), b_n);
+        mix = fmaf(sm_mixw[c], z, mix);
+      }
+    }
+    nws_tc_fence_before();   // TMEM reads ordered before the next tile's first MMA (via the warpgroup barrier)
+    float o = mix + mix_b;
+    if (p.noise_in) o += p.noise_in[(size_t)b * N + n];
+    p.out[(size_t)b * N + n] = ok ? o : __int_as_float(0x7fc00000);
+  }
+  if (!ok && fault) atomicExch(fault, 1);
+  nws_tc_fence_before();
+  __syncthreads();
+  if (tid < 32) nws_tmem_dealloc(tmem_base_s, 64 * kWgs);
+}
+
+}  // namespace
+
+int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
+                        const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
+                        int use_lut, cudaStream_t s) {
+  NwsAudioParams p{};
+  const float* w = ctx->packed;
+  p.f0 = f0; p.carry = carry; p.film = film; p.u_phase = u_phase;
+  p.hmix_wt = w + ctx->lay.hmix_wt; p.hmix_b = w + ctx->lay.hmix_b; p.rand_phase = w + ctx->lay.rand_phase;
+  p.shaper = w + ctx->lay.shaper; p.mix_w = w + ctx->lay.mix_w; p.mix_b = w + ctx->lay.mix_b;
+  p.lut = ctx->lut; p.lut_size = ctx->lut_size; p.lut_min = ctx->lut_min;
+  p.lut_span = ctx->lut_max - ctx->lut_min;
+  p.lut_span_rcp = 1.0f / p.lut_span;
+  p.noise_in = noise_in; p.out = out; p.exciter_out = exciter_out; p.B = B; p.T = T;
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
+    attr_done = true;
+  }
+  const long long tiles = (long long)B * T;
+  const long long want = (tiles + kWgs - 1) / kWgs;
+  const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
+  if (use_lut)
+    nws_audio_tc_kernel<true><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, w + ctx->lay.hmix_umma, nullptr);
+  else
+    nws_audio_tc_kernel<false><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, w + ctx->lay.hmix_umma, nullptr);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}

@@ -37,6 +37,7 @@ struct NwsPackedLayout {
   int proj_wt, proj_b;
   NwsTdMlpOffsets mlp[2];
   int hmix_wt, hmix_b;             // [kHarmPad][64] k-major, [64]
+  int hmix_umma;                   // [2][kHarmPad*64]: tf32 hi / lo parts in the canonical UMMA K-major layout
   int shaper;                      // [64][kShaperStride]
   int mix_w, mix_b;
   int rand_phase;                  // [kHarmPad]
@@ -67,6 +68,7 @@ inline NwsPackedLayout nws_packed_layout() {
   }
   L.hmix_wt = take(kHarmPad * kShapers);
   L.hmix_b = take(kShapers);
+  L.hmix_umma = take(2 * kHarmPad * kShapers);
   L.shaper = take(kShapers * kShaperStride);
   L.mix_w = take(kShapers);
   L.mix_b = take(4);
@@ -101,6 +103,7 @@ struct NwsContext {
   NwsReverbPlan plans[kMaxPlans];
   int n_plans = 0;
   int sm_count = 148;
+  int audio_impl = 1;          // 1 = tcgen05 harmonic mixer (nws_audio_tc.cu), 0 = fp32 SIMT (nws_audio.cu)
   int device = 0;
   // optional per-stage timing of nws_forward (cudaEvents on the launch stream)
   bool profile = false;
@@ -169,6 +172,9 @@ int nws_launch_rng(float* u_phase, float* noise, int n_noise, uint64_t seed, uin
 int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                      const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
                      int use_lut, cudaStream_t s);
+int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
+                        const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
+                        int use_lut, cudaStream_t s);
 int nws_launch_build_lut(const NwsContext* ctx, const float* points, float* lut, int table_size, float tmin,
                          float tmax, cudaStream_t s);
 int nws_launch_pack_weights(NwsContext* ctx, const float* const* tensors, cudaStream_t s);

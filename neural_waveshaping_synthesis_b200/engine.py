@@ -168,6 +168,10 @@ class NwsEngine:
                                                  _ptr(ws), ws.numel(), self._stream()))
         return out
 
+    def set_audio_impl(self, impl: int):
+        """1 = tcgen05 harmonic mixer (default), 0 = fp32 SIMT mixer."""
+        _lib.check(self.lib.nws_set_audio_impl(self.handle, impl))
+
     def set_profiling(self, enable: bool):
         _lib.check(self.lib.nws_set_profiling(self.handle, 1 if enable else 0))
 

@@ -71,23 +71,50 @@ def test_td_mlps(tag, eng_rand, eng_vn):
     assert err(H, c["part_H"])[0] < 2e-5 * max(1.0, float(c["part_H"].abs().max()))
 
 
+def test_tcgen05_selftest():
+    """The tensor-core plumbing (UMMA descriptors, 3xTF32 split, TMEM round trip) against float64."""
+    from neural_waveshaping_synthesis_b200 import _lib
+    lib = _lib.load_library()
+    for K in (8, 48, 104):
+        g = torch.Generator().manual_seed(K)
+        A = (torch.rand(128, K, generator=g) * 2 - 1).cuda()
+        B = (torch.rand(64, K, generator=g) * 0.2 - 0.1).cuda()
+        D = torch.zeros(128, 64, device="cuda")
+        st = torch.zeros(1, dtype=torch.int32, device="cuda")
+        assert lib.nws_selftest_umma(A.data_ptr(), B.data_ptr(), D.data_ptr(), K, 0, st.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        assert int(st[0]) == 1
+        ref = A.double() @ B.double().t()
+        assert (D.double() - ref).abs().max().item() < 4e-6
+
+
+@pytest.mark.parametrize("impl", [1, 0])   # 1 = tcgen05 harmonic mixer (default), 0 = fp32 SIMT mixer
 @pytest.mark.parametrize("tag", ["randinit", "vn"])
-def test_exciter_and_newt(tag, eng_rand, eng_vn):
+def test_exciter_and_newt(tag, impl, eng_rand, eng_vn):
     eng, w = eng_rand if tag == "randinit" else eng_vn
     c = load_case("small_%s_newt" % tag)
-    out, exc = eng.audio(c["f0"].cuda(), c["part_film"].cuda(), c["u_phase"].cuda(), use_lut=False, want_exciter=True)
+    eng.set_audio_impl(impl)
+    try:
+        out, exc = eng.audio(c["f0"].cuda(), c["part_film"].cuda(), c["u_phase"].cuda(), use_lut=False, want_exciter=True)
+    finally:
+        eng.set_audio_impl(1)
     e = err(exc, c["part_exciter"])
     assert e[0] < 2e-5, e
     e = err(out, c["part_newt_out"][:, 0])
     assert e[0] < _tols(tag)[0], e
 
 
+@pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("tag", ["randinit", "vn"])
-def test_fastnewt_stage(tag, eng_rand, eng_vn):
+def test_fastnewt_stage(tag, impl, eng_rand, eng_vn):
     eng, w = eng_rand if tag == "randinit" else eng_vn
     c = load_case("small_%s_fast" % tag)
     eng.set_lut(oracle.build_lookup_table(w))
-    out = eng.audio(c["f0"].cuda(), c["part_film"].cuda(), c["u_phase"].cuda(), use_lut=True)
+    eng.set_audio_impl(impl)
+    try:
+        out = eng.audio(c["f0"].cuda(), c["part_film"].cuda(), c["u_phase"].cuda(), use_lut=True)
+    finally:
+        eng.set_audio_impl(1)
     e = err(out, c["part_newt_out"][:, 0])
     assert e[0] < _tols(tag)[0], e
 
