@@ -67,6 +67,7 @@ extern "C" int nws_destroy(NwsHandle ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaFree(ctx->packed);
   cudaFree(ctx->lut);
+  cudaFree(ctx->lut2);
   cudaFree(ctx->tw_master);
   delete ctx;
   return NWS_OK;
@@ -101,9 +102,12 @@ static int ensure_lut_storage(NwsContext* ctx, int table_size) {
   if (table_size < 2 || table_size > (1 << 20)) { nws_set_error("LUT size %d out of range", table_size); return NWS_ERR_INVALID; }
   if (ctx->lut_size != table_size) {
     cudaFree(ctx->lut);
+    cudaFree(ctx->lut2);
     ctx->lut = nullptr;
+    ctx->lut2 = nullptr;
     ctx->lut_size = 0;
     NWS_CUDA_OK(cudaMalloc(&ctx->lut, (size_t)kShapers * table_size * sizeof(float)));
+    NWS_CUDA_OK(cudaMalloc(&ctx->lut2, (size_t)kShapers * table_size * sizeof(float2)));
     ctx->lut_size = table_size;
   }
   return NWS_OK;
@@ -118,6 +122,8 @@ extern "C" int nws_build_lut(NwsHandle ctx, int table_size, float tmin, float tm
   if (rc) return rc;
   rc = nws_launch_build_lut(ctx, sample_points, ctx->lut, table_size, tmin, tmax, (cudaStream_t)stream);
   if (rc) return rc;
+  rc = nws_launch_pair_lut(ctx, (cudaStream_t)stream);
+  if (rc) return rc;
   ctx->lut_min = tmin; ctx->lut_max = tmax; ctx->lut_valid = true;
   return NWS_OK;
 }
@@ -129,6 +135,8 @@ extern "C" int nws_set_lut(NwsHandle ctx, const float* lut, int table_size, floa
   if (rc) return rc;
   NWS_CUDA_OK(cudaMemcpyAsync(ctx->lut, lut, (size_t)kShapers * table_size * sizeof(float), cudaMemcpyDeviceToDevice,
                               (cudaStream_t)stream));
+  rc = nws_launch_pair_lut(ctx, (cudaStream_t)stream);
+  if (rc) return rc;
   ctx->lut_min = tmin; ctx->lut_max = tmax; ctx->lut_valid = true;
   return NWS_OK;
 }

@@ -115,6 +115,23 @@ __global__ void nws_build_lut_kernel(const float* __restrict__ shaper, const flo
   lut[(size_t)c * table_size + i] = nws_shaper_mlp(shaper + c * kShaperStride, x);
 }
 
+// (T[i], T[min(i+1,size-1)] - T[i]): the difference is the same fp32 subtraction FastNEWT.shaping_fn
+// performs per sample (shaping.py:150), so (U - L) * fract + L stays bit-identical while the fused
+// kernels fetch both operands with one 8-byte load.
+__global__ void nws_pair_lut_kernel(const float* __restrict__ lut, float2* __restrict__ lut2, int size) {
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= size) return;
+  const float lo = lut[(size_t)c * size + i], up = lut[(size_t)c * size + (i + 1 < size ? i + 1 : size - 1)];
+  lut2[(size_t)c * size + i] = make_float2(lo, NWS_ADD(up, -lo));
+}
+
+int nws_launch_pair_lut(NwsContext* ctx, cudaStream_t s) {
+  dim3 grid((ctx->lut_size + 255) / 256, kShapers);
+  nws_pair_lut_kernel<<<grid, 256, 0, s>>>(ctx->lut, ctx->lut2, ctx->lut_size);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}
+
 int nws_launch_build_lut(const NwsContext* ctx, const float* points, float* lut, int table_size, float tmin,
                          float tmax, cudaStream_t s) {
   dim3 grid((table_size + 127) / 128, kShapers);
@@ -255,7 +272,7 @@ int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry
   p.f0 = f0; p.carry = carry; p.film = film; p.u_phase = u_phase;
   p.hmix_wt = w + ctx->lay.hmix_wt; p.hmix_b = w + ctx->lay.hmix_b; p.rand_phase = w + ctx->lay.rand_phase;
   p.shaper = w + ctx->lay.shaper; p.mix_w = w + ctx->lay.mix_w; p.mix_b = w + ctx->lay.mix_b;
-  p.lut = ctx->lut; p.lut_size = ctx->lut_size; p.lut_min = ctx->lut_min;
+  p.lut = ctx->lut; p.lut2 = ctx->lut2; p.lut_size = ctx->lut_size; p.lut_min = ctx->lut_min;
   p.lut_span = ctx->lut_max - ctx->lut_min;
   p.lut_span_rcp = 1.0f / p.lut_span;
   p.noise_in = noise_in; p.out = out; p.exciter_out = exciter_out; p.B = B; p.T = T;

@@ -15,6 +15,7 @@ struct NwsAudioParams {
   const float* mix_w;     // [64]
   const float* mix_b;     // [1]
   const float* lut;       // [64][lut_size]
+  const float2* lut2;     // [64][lut_size] (value, forward difference) pairs
   int lut_size;
   float lut_min, lut_span, lut_span_rcp;
   const float* noise_in;  // [B][N] or null: added to the mixdown (neural_waveshaping.py:85-86)

@@ -30,12 +30,13 @@ struct TcCfg {
   static constexpr int KS = USE_LUT ? 16 : 8;                 // harmonics per A stage
   static constexpr int NST = (kHarmPad + KS - 1) / KS;        // stages per tile (7 or 13)
   static constexpr int kStageBytes = 128 * KS * 4;            // one tf32 part of one stage
-  static constexpr int kChPerLd = USE_LUT ? 4 : 2;            // exciter channels per TMEM load
+  static constexpr int kChPerLd = USE_LUT ? 8 : 2;            // exciter channels per TMEM load
   // dynamic shared memory layout (bytes)
   static constexpr int oW = 0;                                // W_hi | W_lo
   static constexpr int oA = oW + 2 * kWBytes;                 // [wg][stage][hi|lo]
   static constexpr int oFilm = oA + kWgs * 2 * 2 * kStageBytes;  // [wg][3][256] floats
-  static constexpr int oSmall = oFilm + kWgs * 3 * kFilm * 4;    // hmix_b[64] | shift[104] | mix_w[64] floats
+  static constexpr int oCoef = oFilm + kWgs * 3 * kFilm * 4;     // [wg][half][64][8] floats: FiLM lerp coefficients
+  static constexpr int oSmall = oCoef + kWgs * 2 * kShapers * 8 * 4;  // hmix_b[64] | shift[104] | mix_w[64] floats
   static constexpr int oShaper = oSmall + (kShapers + kHarmPad + kShapers) * 4;
   static constexpr int kBytes = oShaper + (USE_LUT ? 0 : kShapers * kShaperStride * 4);
 };
@@ -60,7 +61,18 @@ __device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float* v) {
   v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
 }
 
-template <bool USE_LUT>
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <bool USE_LUT, bool TAP>
 __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAudioParams p, const float* __restrict__ w_umma,
                                                                      int* __restrict__ fault) {
   using C = TcCfg<USE_LUT>;
@@ -72,20 +84,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, lane = tid & 31, wwarp = wt >> 5;
   const int T = p.T, N = T * kHop;
   float* sm_small = reinterpret_cast<float*>(smem + C::oSmall);
-  float* sm_hb = sm_small;
-  float* sm_shift = sm_small + kShapers;
-  float* sm_mixw = sm_shift + kHarmPad;
+  float2* sm_bw = reinterpret_cast<float2*>(sm_small);   // [64] (harmonic_mixer bias, mixdown weight)
+  float* sm_shift = sm_small + 2 * kShapers;
   float* sm_film = reinterpret_cast<float*>(smem + C::oFilm) + wg * 3 * kFilm;
+  float* sm_coef = reinterpret_cast<float*>(smem + C::oCoef) + wg * 2 * kShapers * 8;
   float* sm_shaper = reinterpret_cast<float*>(smem + C::oShaper);
   unsigned char* a_base = smem + C::oA + wg * 4 * C::kStageBytes;   // [stage][hi|lo]
 
   // ---- CTA-lifetime staging
   for (int i = tid; i < 2 * kWBytes / 16; i += kTcThreads)
     reinterpret_cast<float4*>(smem + C::oW)[i] = reinterpret_cast<const float4*>(w_umma)[i];
-  if (tid < kShapers) {
-    sm_hb[tid] = p.hmix_b[tid];
-    sm_mixw[tid] = p.mix_w[tid];
-  }
+  if (tid < kShapers) sm_bw[tid] = make_float2(p.hmix_b[tid], p.mix_w[tid]);
   if (tid < kHarmPad) sm_shift[tid] = tid < kHarm ? nws_phase_shift(p.u_phase[tid], p.rand_phase[tid]) : 0.f;
   if (!USE_LUT)
     for (int i = tid; i < kShapers * kShaperStride / 4; i += kTcThreads)
@@ -136,11 +145,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     for (int w = 0; w < wwarp; ++w) pre += warp_tot[wg][w];
     const float csum = (float)(pre + v);
     const float phase = nws_phase_from_cumsum(csum, (float)kSampleRate);
+    {
+      // FiLM upsample (shaping.py:69) as A + l1*(B - A): every sample of a half-hop blends the same two
+      // frames, so the per-channel pairs (A, B-A) of the four FiLM parameters are tabulated once per tile
+      // (thread = (half, channel)); the film frames were published by the barrier above
+      const int h = wt >> 6, c = wt & 63;
+      const int sa = h == 0 ? (t >= 1 ? 0 : 1) : 1;
+      const int sb = h == 0 ? (t >= 1 ? 1 : 2) : (t + 1 < T ? 2 : 1);
+      const float* fa = sm_film + sa * kFilm + c;
+      const float* fb = sm_film + sb * kFilm + c;
+      float4 lo4, hi4;
+      lo4.x = fa[0]; lo4.y = fb[0] - fa[0];
+      lo4.z = fa[kShapers]; lo4.w = fb[kShapers] - fa[kShapers];
+      hi4.x = fa[2 * kShapers]; hi4.y = fb[2 * kShapers] - fa[2 * kShapers];
+      hi4.z = fa[3 * kShapers]; hi4.w = fb[3 * kShapers] - fa[3 * kShapers];
+      float4* dst = reinterpret_cast<float4*>(sm_coef + (h * kShapers + c) * 8);
+      dst[0] = lo4;
+      dst[1] = hi4;
+    }
 
     // ---- oscillator bank -> A operand stages -> tcgen05.mma
 #pragma unroll 1
     for (int st = 0; st < C::NST; ++st) {
       const int buf = st & 1, k0 = st * C::KS;
+      const float k0f = (float)k0;
       const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;   // last stage may be short
       const uint32_t prior = buf ? uses1 : uses0;
       if (prior > 0 && ok) ok = nws_mbar_wait(&bars[wg][buf], (prior - 1) & 1);   // MMAs that read this buffer are done
@@ -152,12 +180,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
           float h[4], l[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int k = k0 + kk + j + 1;   // harmonic number
-            float s = 0.f;
-            if (k <= kHarm) {
-              s = nws_sinf(nws_harmonic_arg(k, phase, sm_shift[k - 1]));
-              s = NWS_MUL(f0u, (float)k) < 0.5f * kSampleRate ? s : 0.f;
-            }
+            // harmonic number k = k0 + kk + j + 1 (k0f + const is exact: small integers).  Harmonics 102..104
+            // are padding: their mixer weights are zero, so their (finite) sines are never seen.
+            const float kf = k0f + (float)(kk + j + 1);
+            float s = nws_sinf(NWS_ADD(NWS_MUL(kf, phase), sm_shift[k0 + kk + j]));   // generators.py:60-61
+            s = NWS_MUL(f0u, kf) < 0.5f * kSampleRate ? s : 0.f;                       // generators.py:50-52
             h[j] = nws_tf32_hi(s);
             l[j] = nws_tf32_lo(s, h[j]);
           }
@@ -194,33 +221,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     }
 
     // ---- FiLM -> shaper -> FiLM -> mixdown (shaping.py:67-79), exciter read from this thread's TMEM lane
-    const float* fa = sm_film + (lc.i0 - (t - 1)) * kFilm;
-    const float* fb = sm_film + (lc.i1 - (t - 1)) * kFilm;
+    const float4* cf = reinterpret_cast<const float4*>(sm_coef + (wt >> 6) * kShapers * 8);
+    const float l1 = lc.l1;
+    const int lut_size = p.lut_size;
+    const float lut_min = p.lut_min, lut_span = p.lut_span, lut_rcp = p.lut_span_rcp;
     float mix = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < kShapers; c0 += C::kChPerLd) {
       float ev[C::kChPerLd];
       tmem_ld<C::kChPerLd>(tmem_lane + c0, ev);
+      const float2* row = p.lut2 + (size_t)c0 * lut_size;
 #pragma unroll
       for (int i = 0; i < C::kChPerLd; ++i) {
         const int c = c0 + i;
-        const float e = ev[i] + sm_hb[c];
-        if (p.exciter_out) p.exciter_out[((size_t)b * kShapers + c) * N + n] = e;
-        const float g_i = nws_lerp_apply(lc, fa[c], fb[c]);
-        const float b_i = nws_lerp_apply(lc, fa[kShapers + c], fb[kShapers + c]);
-        const float g_n = nws_lerp_apply(lc, fa[2 * kShapers + c], fb[2 * kShapers + c]);
-        const float b_n = nws_lerp_apply(lc, fa[3 * kShapers + c], fb[3 * kShapers + c]);
+        const float2 bw = sm_bw[c];
+        const float e = ev[i] + bw.x;
+        if (TAP) p.exciter_out[((size_t)b * kShapers + c) * N + n] = e;
+        const float4 ci = cf[2 * c], cn = cf[2 * c + 1];
+        const float g_i = fmaf(l1, ci.y, ci.x), b_i = fmaf(l1, ci.w, ci.z);
+        const float g_n = fmaf(l1, cn.y, cn.x), b_n = fmaf(l1, cn.w, cn.z);
         const float x = NWS_ADD(NWS_MUL(g_i, e), b_i);
         float y;
         if (USE_LUT) {
-          const NwsLutIdx li = nws_lut_index(x, p.lut_size, p.lut_min, p.lut_span, p.lut_span_rcp);
-          const float* row = p.lut + (size_t)c * p.lut_size;
-          y = nws_lut_lerp(__ldg(row + li.lower), __ldg(row + li.upper), li.fract);
+          // FastNEWT.shaping_fn (shaping.py:136-151): same index arithmetic as nws_lut_index; the table row
+          // holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
+          const float idx = nws_div_markstein(NWS_MUL((float)lut_size, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
+          float fl = floorf(idx);
+          fl = fminf(fmaxf(fl, 0.0f), (float)(lut_size - 1));
+          const float2 t2 = __ldg(row + (size_t)i * lut_size + (int)fl);
+          y = NWS_ADD(NWS_MUL(t2.y, NWS_ADD(idx, -fl)), t2.x);
         } else {
           y = nws_shaper_mlp(sm_shaper + c * kShaperStride, x);
         }
         const float z = NWS_ADD(NWS_MUL(g_n, y), b_n);
-        mix = fmaf(sm_mixw[c], z, mix);
+        mix = fmaf(bw.y, z, mix);
       }
     }
     nws_tc_fence_before();   // TMEM reads ordered before the next tile's first MMA (via the warpgroup barrier)
@@ -244,24 +278,27 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   p.f0 = f0; p.carry = carry; p.film = film; p.u_phase = u_phase;
   p.hmix_wt = w + ctx->lay.hmix_wt; p.hmix_b = w + ctx->lay.hmix_b; p.rand_phase = w + ctx->lay.rand_phase;
   p.shaper = w + ctx->lay.shaper; p.mix_w = w + ctx->lay.mix_w; p.mix_b = w + ctx->lay.mix_b;
-  p.lut = ctx->lut; p.lut_size = ctx->lut_size; p.lut_min = ctx->lut_min;
+  p.lut = ctx->lut; p.lut2 = ctx->lut2; p.lut_size = ctx->lut_size; p.lut_min = ctx->lut_min;
   p.lut_span = ctx->lut_max - ctx->lut_min;
   p.lut_span_rcp = 1.0f / p.lut_span;
   p.noise_in = noise_in; p.out = out; p.exciter_out = exciter_out; p.B = B; p.T = T;
 
   static bool attr_done = false;
   if (!attr_done) {
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
     attr_done = true;
   }
   const long long tiles = (long long)B * T;
   const long long want = (tiles + kWgs - 1) / kWgs;
   const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
-  if (use_lut)
-    nws_audio_tc_kernel<true><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, w + ctx->lay.hmix_umma, nullptr);
-  else
-    nws_audio_tc_kernel<false><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, w + ctx->lay.hmix_umma, nullptr);
+  const float* wu = w + ctx->lay.hmix_umma;
+  if (use_lut && !exciter_out) nws_audio_tc_kernel<true, false><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
+  else if (use_lut) nws_audio_tc_kernel<true, true><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
+  else if (!exciter_out) nws_audio_tc_kernel<false, false><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
+  else nws_audio_tc_kernel<false, true><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }

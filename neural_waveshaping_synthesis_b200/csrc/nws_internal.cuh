@@ -96,6 +96,7 @@ struct NwsContext {
   float* packed = nullptr;     // device weight blob
   bool weights_loaded = false;
   float* lut = nullptr;        // [64][table_size]
+  float2* lut2 = nullptr;      // [64][table_size] pairs (T[i], T[min(i+1,size-1)] - T[i]) for the fused kernels
   int lut_size = 0;
   float lut_min = 0.f, lut_max = 0.f;
   bool lut_valid = false;
@@ -175,6 +176,7 @@ int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
                         int use_lut, cudaStream_t s);
+int nws_launch_pair_lut(NwsContext* ctx, cudaStream_t s);
 int nws_launch_build_lut(const NwsContext* ctx, const float* points, float* lut, int table_size, float tmin,
                          float tmax, cudaStream_t s);
 int nws_launch_pack_weights(NwsContext* ctx, const float* const* tensors, cudaStream_t s);
