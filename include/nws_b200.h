@@ -181,6 +181,14 @@ int nws_set_profiling(NwsHandle handle, int enable);
 /* Waits for the recorded events and writes the last forward's stage times (ms) to ms_out[0..9]. */
 int nws_get_stage_times(NwsHandle handle, float* ms_out, int n);
 
+/* control [B,C,T] -> film [B,256,T], bands [B,129,T]: get_embedding + ControlModule + newt.mlp +
+ * h_generator (neural_waveshaping.py:69-72,78,82; shaping.py:68) — the whole hop-rate chain. */
+int nws_stage_control_to_params(NwsHandle handle, const float* control, int ctrl_channels, float* film_out,
+                                float* bands_out, int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+/* Implementation of the hop-rate MLP chain: 1 (default) = one tcgen05 kernel, activations in TMEM, weights
+ * streamed by cp.async.bulk (csrc/nws_mlp_tc.cu); 0 = fp32 SIMT layer kernels (csrc/nws_encoder.cu). */
+int nws_set_mlp_impl(NwsHandle handle, int impl);
+
 /* Implementation of the fused audio-rate kernel's harmonic mixer: 1 (default) = tcgen05 3xTF32 with
  * the accumulator in TMEM (csrc/nws_audio_tc.cu), 0 = fp32 SIMT (csrc/nws_audio.cu, kept as the
  * in-library cross-check). */

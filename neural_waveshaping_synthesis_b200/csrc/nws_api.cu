@@ -49,6 +49,7 @@ extern "C" int nws_create(const NwsConfig* cfg, NwsHandle* out) {
   cudaError_t e = cudaGetDevice(&ctx->device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->packed, (size_t)ctx->lay.total * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->mlp_tc, nws_mlp_tc_blob_floats() * sizeof(float));
   if (e != cudaSuccess) {
     nws_set_error("nws_create: %s (a CUDA device is required; there is no CPU fallback)", cudaGetErrorString(e));
     delete ctx;
@@ -66,6 +67,7 @@ extern "C" int nws_destroy(NwsHandle ctx) {
   for (int i = 0; i < 2 * kStCount; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaFree(ctx->packed);
+  cudaFree(ctx->mlp_tc);
   cudaFree(ctx->lut);
   cudaFree(ctx->lut2);
   cudaFree(ctx->tw_master);
@@ -91,6 +93,8 @@ extern "C" int nws_load_weights(NwsHandle ctx, const float* const* tensors, int 
     }
   }
   int rc = nws_launch_pack_weights(ctx, tensors, s);
+  if (rc) return rc;
+  rc = nws_launch_mlp_tc_pack(ctx, tensors, s);
   if (rc) return rc;
   ctx->weights_loaded = true;
   ctx->lut_valid = false;
@@ -219,6 +223,35 @@ static int launch_audio(const NwsContext* ctx, const float* f0, const double* ca
                          : nws_launch_audio(ctx, f0, carry, film, u_phase, noise_in, out, exciter_out, B, T, use_lut, s);
 }
 
+extern "C" int nws_set_mlp_impl(NwsHandle ctx, int impl) {
+  if (!ctx || (impl != 0 && impl != 1)) { nws_set_error("nws_set_mlp_impl: impl must be 0 (fp32 SIMT layers) or 1 (tcgen05 chain)"); return NWS_ERR_INVALID; }
+  ctx->mlp_impl = impl;
+  return NWS_OK;
+}
+
+// control -> (FiLM parameters, noise band gains): get_embedding + ControlModule + both TimeDistributedMLPs
+// (neural_waveshaping.py:69-72,78; shaping.py:68; neural_waveshaping.py:82), reference layouts.
+extern "C" int nws_stage_control_to_params(NwsHandle ctx, const float* control, int ctrl_channels, float* film_out,
+                                           float* bands_out, int B, int T, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+  NwsWorkspace w;
+  NWS_TRY(check_common(ctx, B, T, workspace, workspace_bytes, "nws_stage_control_to_params", &w));
+  if (!control || !film_out || !bands_out || ctrl_channels < 2) { nws_set_error("nws_stage_control_to_params: bad argument"); return NWS_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int M = B * T;
+  NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, s));
+  if (ctx->mlp_impl) {
+    NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, s));
+  } else {
+    NWS_TRY(nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b, nullptr, nullptr,
+                              w.emb, M, kEmb, kEmb, kEmb, false, s));
+    NWS_TRY(nws_launch_td_mlp(ctx, NWS_MLP_FILM, w.emb, w.act0, w.act1, w.film, M, s));
+    NWS_TRY(nws_launch_td_mlp(ctx, NWS_MLP_NOISE, w.emb, w.act0, w.act1, w.bands, M, s));
+  }
+  NWS_TRY(nws_launch_rows_to_bct(w.film, film_out, B, kFilm, T, kFilm, s));
+  return nws_launch_rows_to_bct(w.bands, bands_out, B, kBands, T, kBandsPad, s);
+}
+
 extern "C" int nws_set_audio_impl(NwsHandle ctx, int impl) {
   if (!ctx || (impl != 0 && impl != 1)) { nws_set_error("nws_set_audio_impl: impl must be 0 (fp32 SIMT mixer) or 1 (tcgen05 mixer)"); return NWS_ERR_INVALID; }
   ctx->audio_impl = impl;
@@ -265,10 +298,15 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   // hop rate: phase carries, control encoder, FiLM parameters, noise band gains
   NWS_STAGE(ctx, kStCarry, s, nws_launch_phase_carry(f0, w.carry, B, T, s));
   NWS_STAGE(ctx, kStGru, s, nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, s));
-  NWS_STAGE(ctx, kStProj, s, nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b,
-                                               nullptr, nullptr, w.emb, M, kEmb, kEmb, kEmb, false, s));
-  NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_td_mlp(ctx, NWS_MLP_FILM, w.emb, w.act0, w.act1, w.film, M, s));
-  NWS_STAGE(ctx, kStMlpNoise, s, nws_launch_td_mlp(ctx, NWS_MLP_NOISE, w.emb, w.act0, w.act1, w.bands, M, s));
+  if (ctx->mlp_impl) {
+    // projection + both TimeDistributedMLPs in one tensor-core kernel (activations stay in TMEM)
+    NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, s));
+  } else {
+    NWS_STAGE(ctx, kStProj, s, nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b,
+                                                 nullptr, nullptr, w.emb, M, kEmb, kEmb, kEmb, false, s));
+    NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_td_mlp(ctx, NWS_MLP_FILM, w.emb, w.act0, w.act1, w.film, M, s));
+    NWS_STAGE(ctx, kStMlpNoise, s, nws_launch_td_mlp(ctx, NWS_MLP_NOISE, w.emb, w.act0, w.act1, w.bands, M, s));
+  }
   // noise branch -> dry
   NWS_STAGE(ctx, kStNoiseSpec, s, nws_launch_noise_spectrum(ctx, noise, w.xspec, T, s));
   NWS_STAGE(ctx, kStNoiseFilter, s, nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, s));

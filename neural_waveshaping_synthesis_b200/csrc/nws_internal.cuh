@@ -104,6 +104,9 @@ struct NwsContext {
   NwsReverbPlan plans[kMaxPlans];
   int n_plans = 0;
   int sm_count = 148;
+  int mlp_impl = 1;            // 1 = tcgen05 MLP chain (nws_mlp_tc.cu), 0 = fp32 SIMT layers (nws_encoder.cu)
+  float* mlp_tc = nullptr;     // TC weight blob (hi/lo parts, canonical UMMA layout, chunked)
+  int mlp_tc_off[11] = {};
   int audio_impl = 1;          // 1 = tcgen05 harmonic mixer (nws_audio_tc.cu), 0 = fp32 SIMT (nws_audio.cu)
   int device = 0;
   // optional per-stage timing of nws_forward (cudaEvents on the launch stream)
@@ -176,6 +179,9 @@ int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
                         int use_lut, cudaStream_t s);
+size_t nws_mlp_tc_blob_floats();
+int nws_launch_mlp_tc_pack(NwsContext* ctx, const float* const* tensors, cudaStream_t s);
+int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, cudaStream_t s);
 int nws_launch_pair_lut(NwsContext* ctx, cudaStream_t s);
 int nws_launch_build_lut(const NwsContext* ctx, const float* points, float* lut, int table_size, float tmin,
                          float tmax, cudaStream_t s);

@@ -1,0 +1,391 @@
+// Hop-rate MLP chain on the tensor cores: embedding projection + the two TimeDistributedMLPs
+// (neural_waveshaping.py:22,26; dynamic.py:20-40; shaping.py:53-55,68; neural_waveshaping.py:58,82)
+// for a tile of 128 frames in ONE kernel, activations never leaving the SM:
+//
+//   A operand  = activations, in TENSOR MEMORY (lane = frame, column = channel), tf32 hi / lo parts
+//   B operand  = weights, streamed from L2 into a shared-memory ring by cp.async.bulk (1-D TMA),
+//                pre-split into tf32 hi / lo and pre-arranged in the canonical UMMA K-major layout
+//   D          = accumulator in TMEM (two 128-column regions, alternating per weight block)
+//   D += A_hi B_hi + A_lo B_hi + A_hi B_lo  (3xTF32: fp32-level accuracy)
+//   epilogue   = each thread owns one frame row: TMEM -> registers, bias, LayerNorm over the row's 128
+//                channels entirely in-thread, LeakyReLU, hi/lo split, tcgen05.st back as the next A
+//
+// Warp roles (192 threads): warps 0-3 epilogue warpgroup (thread = frame), warp 4 weight producer,
+// warp 5 MMA issuer.  Block sequence per tile: proj, A1, A2, A3, Aout[0:128], Aout[128:256],
+// proj (again, from a reload of the GRU states), B1, B2, B3, Bout[0:128], Bout[128:144].
+#include "nws_internal.cuh"
+#include "nws_tc.cuh"
+
+namespace {
+
+constexpr int kMlpThreads = 192;
+constexpr int kSlots = 4;
+constexpr int kChunkK = 32;                 // K elements per ring chunk (4 MMA k-steps)
+constexpr int kSlotBytes = 2 * 128 * kChunkK * 4;  // hi + lo of a [128 x 32] chunk = 32 KB
+constexpr int kBlocks = 12;
+constexpr uint32_t kColAhi = 0, kColAlo = 128, kColD = 256;
+
+struct MlpBlockDesc {
+  int w_off;     // float offset of the block's chunks inside the TC weight blob
+  int n;         // MMA N (128 or 16)
+  int kind;      // 0: +bias -> next A (proj)   1: +bias, LN, LeakyReLU -> next A
+                 // 2: +bias -> film[:, col0:col0+128]   3: +bias -> bands[:, col0 : col0+n_store]
+  int col0;      // output column offset for kinds 2/3
+  int new_a;     // 1 if this block needs an A version published after the previous block's epilogue
+  int n_bias;    // valid bias entries
+  int bias, g, beta;  // float offsets into the packed blob (copied to shared memory at kernel start)
+};
+constexpr int kVecStride = 3 * 128;   // per block: bias[128] | gamma[128] | beta[128]
+
+struct MlpTcParams {
+  MlpBlockDesc blk[kBlocks];
+  const float* packed;    // ctx->packed (bias / LN vectors)
+  const float* w_tc;      // TC weight blob
+  const float* h;         // [M][128] GRU states
+  float* film;            // [M][256]
+  float* bands;           // [M][132]
+  int M;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nws_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nws_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   nws_smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(nws_smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+      "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+      "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+      "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// write 16 activations (columns c0..c0+15 of this thread's row) as the next A operand: hi and lo parts
+__device__ __forceinline__ void store_a16(uint32_t tmem_row, int c0, const float* y) {
+  float hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    hi[i] = nws_tf32_hi(y[i]);
+    lo[i] = nws_tf32_lo(y[i], hi[i]);
+  }
+  tmem_st16(tmem_row + kColAhi + c0, hi);
+  tmem_st16(tmem_row + kColAlo + c0, lo);
+}
+
+__global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcParams p, int* __restrict__ fault) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[kSlots], empty_bar[kSlots], a_ready, d_ready[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int fault_s;
+  __shared__ __align__(16) float vec_s[kBlocks * kVecStride];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (p.M + 127) / 128;
+  for (int i = tid; i < kBlocks * kVecStride; i += kMlpThreads) {
+    const int b = i / kVecStride, r = i % kVecStride, which = r >> 7, c = r & 127;
+    const MlpBlockDesc& d = p.blk[b];
+    float v = 0.f;
+    if (which == 0) v = c < d.n_bias ? p.packed[d.bias + c] : 0.f;
+    else if (d.kind == 1) v = p.packed[(which == 1 ? d.g : d.beta) + c];
+    vec_s[i] = v;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < kSlots; ++s) { nws_mbar_init(&full_bar[s], 1); nws_mbar_init(&empty_bar[s], 1); }
+    nws_mbar_init(&a_ready, 128);
+    nws_mbar_init(&d_ready[0], 1);
+    nws_mbar_init(&d_ready[1], 1);
+    nws_fence_mbar_init();
+    fault_s = 0;
+  }
+  if (warp == 0) nws_tmem_alloc(&tmem_base_s, 512);
+  nws_tc_fence_before();
+  __syncthreads();
+  nws_tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 4) {
+    // ================= weight producer: one lane streams every block's chunks through the ring
+    if (lane == 0) {
+      uint32_t n_fill = 0;   // chunks issued so far (slot = n_fill % kSlots)
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        for (int b = 0; b < kBlocks && ok; ++b) {
+          const MlpBlockDesc d = p.blk[b];
+          const uint32_t chunk_bytes = 2u * d.n * kChunkK * 4u;
+          for (int ck = 0; ck < kEmb / kChunkK && ok; ++ck, ++n_fill) {
+            const int s = n_fill % kSlots;
+            const uint32_t use = n_fill / kSlots;
+            if (use > 0) ok = nws_mbar_wait(&empty_bar[s], (use - 1) & 1);
+            if (!ok) break;
+            mbar_expect_tx(&full_bar[s], chunk_bytes);
+            bulk_g2s(smem + s * kSlotBytes, p.w_tc + d.w_off + (size_t)ck * (chunk_bytes / 4), chunk_bytes, &full_bar[s]);
+          }
+        }
+      }
+      if (!ok) fault_s = 1;
+    }
+  } else if (warp == 5) {
+    // ================= MMA issuer
+    if (lane == 0) {
+      uint32_t n_use = 0, a_ver = 0, n_blk = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        for (int b = 0; b < kBlocks && ok; ++b, ++n_blk) {
+          const MlpBlockDesc d = p.blk[b];
+          if (d.new_a) {   // wait for the epilogue warpgroup to publish this block's A
+            ok = nws_mbar_wait(&a_ready, a_ver & 1);
+            ++a_ver;
+            if (!ok) break;
+          }
+          nws_tc_fence_after();
+          const uint32_t idesc = nws_umma_idesc_tf32(128, d.n);
+          const uint32_t lbo = (uint32_t)(d.n / 8) * 128u, part = (uint32_t)d.n * kChunkK * 4u;
+          const uint32_t dcol = tmem + kColD + (n_blk & 1) * 128;
+          for (int ck = 0; ck < kEmb / kChunkK && ok; ++ck, ++n_use) {
+            const int s = n_use % kSlots;
+            ok = nws_mbar_wait(&full_bar[s], (n_use / kSlots) & 1);
+            if (!ok) break;
+            nws_tc_fence_after();
+            const uint32_t sb = nws_smem_u32(smem + s * kSlotBytes);
+#pragma unroll
+            for (int j = 0; j < kChunkK / 8; ++j) {
+              const uint32_t acol = ck * kChunkK + j * 8;
+              const uint64_t bh = nws_umma_smem_desc(sb + j * 2 * lbo, lbo, 128);
+              const uint64_t bl = nws_umma_smem_desc(sb + part + j * 2 * lbo, lbo, 128);
+              umma_tf32_ts(dcol, tmem + kColAhi + acol, bh, idesc, (ck | j) ? 1u : 0u);
+              umma_tf32_ts(dcol, tmem + kColAlo + acol, bh, idesc, 1u);
+              umma_tf32_ts(dcol, tmem + kColAhi + acol, bl, idesc, 1u);
+            }
+            nws_umma_commit(&empty_bar[s]);   // slot reusable once these MMAs have read it
+          }
+          if (ok) nws_umma_commit(&d_ready[n_blk & 1]);
+        }
+      }
+      if (!ok) fault_s = 1;
+    }
+  } else {
+    // ================= epilogue warpgroup: thread = frame row = TMEM lane
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t n_blk = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+      const int row = tile * 128 + tid;
+      const bool valid = row < p.M;
+      const float* hrow = p.h + (size_t)(valid ? row : 0) * kEmb;
+      for (int b = 0; b < kBlocks && ok; ++b, ++n_blk) {
+        const MlpBlockDesc d = p.blk[b];
+        if (b == 0 || b == 6) {
+          // A <- this frame's GRU state (the embedding projection's input), hi/lo split
+#pragma unroll 1
+          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+            float y[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 v = valid ? *reinterpret_cast<const float4*>(hrow + c0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+              y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
+            }
+            store_a16(tmem_row, c0, y);
+          }
+          tmem_wait_st();
+          nws_tc_fence_before();
+          mbar_arrive(&a_ready);
+        }
+        // wait for this block's accumulator
+        ok = nws_mbar_wait(&d_ready[n_blk & 1], (n_blk >> 1) & 1);
+        if (!ok) break;
+        nws_tc_fence_after();
+        const uint32_t drow = tmem_row + kColD + (n_blk & 1) * 128;
+        const float* bias = vec_s + b * kVecStride;
+        if (d.kind == 1) {
+          const float* g = bias + 128;
+          const float* be = bias + 256;
+          float sum = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+            float v[16];
+            nws_tmem_ld16(drow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sum += v[i] + bias[c0 + i];
+          }
+          const float mean = sum * (1.0f / kEmb);
+          float q = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+            float v[16];
+            nws_tmem_ld16(drow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { const float dd = (v[i] + bias[c0 + i]) - mean; q = fmaf(dd, dd, q); }
+          }
+          const float rstd = 1.0f / sqrtf(q * (1.0f / kEmb) + 1e-5f);
+#pragma unroll 1
+          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+            float v[16], y[16];
+            nws_tmem_ld16(drow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float t = fmaf(((v[i] + bias[c0 + i]) - mean) * rstd, g[c0 + i], be[c0 + i]);
+              y[i] = t > 0.f ? t : 0.01f * t;
+            }
+            store_a16(tmem_row, c0, y);
+          }
+          tmem_wait_st();
+          nws_tc_fence_before();
+          mbar_arrive(&a_ready);
+        } else if (d.kind == 0) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+            float v[16];
+            nws_tmem_ld16(drow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += bias[c0 + i];
+            store_a16(tmem_row, c0, v);
+          }
+          tmem_wait_st();
+          nws_tc_fence_before();
+          mbar_arrive(&a_ready);
+        } else {
+          const bool film = d.kind == 2;
+          float* orow = film ? p.film + (size_t)(valid ? row : 0) * kFilm + d.col0
+                             : p.bands + (size_t)(valid ? row : 0) * kBandsPad + d.col0;
+          const int n_store = film ? 128 : (d.n == 128 ? 128 : kBandsPad - 128);
+#pragma unroll 1
+          for (int c0 = 0; c0 < d.n; c0 += 16) {
+            float v[16];
+            nws_tmem_ld16(drow + c0, v);
+            if (valid) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (c0 + 4 * q < n_store) {
+                  float4 o;
+                  o.x = v[4 * q] + bias[c0 + 4 * q]; o.y = v[4 * q + 1] + bias[c0 + 4 * q + 1];
+                  o.z = v[4 * q + 2] + bias[c0 + 4 * q + 2]; o.w = v[4 * q + 3] + bias[c0 + 4 * q + 3];
+                  *reinterpret_cast<float4*>(orow + c0 + 4 * q) = o;
+                }
+              }
+            }
+          }
+          nws_tc_fence_before();
+        }
+      }
+    }
+    if (!ok) fault_s = 1;
+  }
+  nws_tc_fence_before();
+  __syncthreads();
+  if (fault_s && fault && tid == 0) atomicExch(fault, 1);
+  if (warp == 0) nws_tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TC weight blob: for each weight block, chunks of 32 K-columns, each chunk = [hi part | lo part],
+// each part in the canonical no-swizzle K-major layout of an [n x 32] operand.
+struct MlpTcPackArgs {
+  const float* w[11];   // source weights [n_rows][128] (PyTorch layout), 11 distinct blocks
+  int row0[11];         // first source row of the block
+  int rows_valid[11];   // rows beyond this are zero padding
+  int n[11];            // block N (128 or 16)
+  int off[11];          // float offset of the block in the blob
+  int total;
+};
+
+__global__ void nws_mlp_tc_pack_kernel(MlpTcPackArgs a, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  int b = 0;
+  while (b + 1 < 11 && i >= a.off[b + 1]) ++b;
+  const int n = a.n[b], j = i - a.off[b];
+  const int chunk_floats = 2 * n * kChunkK;
+  const int ck = j / chunk_floats, r = j % chunk_floats;
+  const int part = r / (n * kChunkK), q = r % (n * kChunkK);
+  const int per_kc = (n / 8) * 32;                  // floats per 16-byte k-chunk column of core matrices
+  const int kc = q / per_kc, rem = q % per_kc;
+  const int row = (rem / 32) * 8 + ((rem & 31) >> 2), k = ck * kChunkK + kc * 4 + (rem & 3);
+  const float w = row < a.rows_valid[b] ? a.w[b][(size_t)(a.row0[b] + row) * kEmb + k] : 0.f;
+  const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+  dst[i] = part == 0 ? hi : __uint_as_float(__float_as_uint(w - hi) & 0xffffe000u);
+}
+
+}  // namespace
+
+size_t nws_mlp_tc_blob_floats() { return (size_t)10 * 2 * 128 * kEmb + (size_t)2 * 16 * kEmb; }
+
+int nws_launch_mlp_tc_pack(NwsContext* ctx, const float* const* tensors, cudaStream_t s) {
+  MlpTcPackArgs a{};
+  // distinct blocks: proj, A1, A2, A3, Aout[0:128], Aout[128:256], B1, B2, B3, Bout[0:128], Bout[128:144]
+  const float* src[11] = {tensors[NWS_T_PROJ_W],
+                          tensors[NWS_T_FILM_MLP + 0], tensors[NWS_T_FILM_MLP + 4], tensors[NWS_T_FILM_MLP + 8],
+                          tensors[NWS_T_FILM_MLP + 12], tensors[NWS_T_FILM_MLP + 12],
+                          tensors[NWS_T_NOISE_MLP + 0], tensors[NWS_T_NOISE_MLP + 4], tensors[NWS_T_NOISE_MLP + 8],
+                          tensors[NWS_T_NOISE_MLP + 12], tensors[NWS_T_NOISE_MLP + 12]};
+  const int row0[11] = {0, 0, 0, 0, 0, 128, 0, 0, 0, 0, 128};
+  const int rows_valid[11] = {128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 1};
+  const int nn[11] = {128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 16};
+  int off = 0;
+  for (int b = 0; b < 11; ++b) {
+    a.w[b] = src[b]; a.row0[b] = row0[b]; a.rows_valid[b] = rows_valid[b]; a.n[b] = nn[b]; a.off[b] = off;
+    ctx->mlp_tc_off[b] = off;
+    off += 2 * nn[b] * kEmb;
+  }
+  a.total = off;
+  nws_mlp_tc_pack_kernel<<<(off + 255) / 256, 256, 0, s>>>(a, ctx->mlp_tc);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}
+
+int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, cudaStream_t s) {
+  MlpTcParams p{};
+  const NwsPackedLayout& L = ctx->lay;
+  // block -> (distinct weight block, N, kind, col0, new_a, bias, gamma, beta)
+  const int wsel[kBlocks] = {0, 1, 2, 3, 4, 5, 0, 6, 7, 8, 9, 10};
+  const int nn[kBlocks] = {128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 16};
+  const int kind[kBlocks] = {0, 1, 1, 1, 2, 2, 0, 1, 1, 1, 3, 3};
+  const int col0[kBlocks] = {0, 0, 0, 0, 0, 128, 0, 0, 0, 0, 0, 128};
+  const int new_a[kBlocks] = {1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 0};
+  for (int b = 0; b < kBlocks; ++b) {
+    MlpBlockDesc& d = p.blk[b];
+    d.w_off = ctx->mlp_tc_off[wsel[b]]; d.n = nn[b]; d.kind = kind[b]; d.col0 = col0[b]; d.new_a = new_a[b];
+    d.g = d.beta = 0;
+    d.n_bias = 128;
+  }
+  p.blk[11].n_bias = kBandsPad - 128;
+  p.blk[0].bias = p.blk[6].bias = L.proj_b;
+  for (int l = 0; l < 3; ++l) {
+    p.blk[1 + l].bias = L.mlp[0].b[l]; p.blk[1 + l].g = L.mlp[0].g[l]; p.blk[1 + l].beta = L.mlp[0].beta[l];
+    p.blk[7 + l].bias = L.mlp[1].b[l]; p.blk[7 + l].g = L.mlp[1].g[l]; p.blk[7 + l].beta = L.mlp[1].beta[l];
+  }
+  p.blk[4].bias = L.mlp[0].b_out; p.blk[5].bias = L.mlp[0].b_out + 128;
+  p.blk[10].bias = L.mlp[1].b_out; p.blk[11].bias = L.mlp[1].b_out + 128;
+  p.packed = ctx->packed; p.w_tc = ctx->mlp_tc; p.h = hbuf; p.film = film; p.bands = bands; p.M = M;
+
+  static bool attr_done = false;
+  const int smem = kSlots * kSlotBytes;
+  if (!attr_done) {
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  const int tiles = (M + 127) / 128;
+  const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  nws_mlp_tc_kernel<<<grid, kMlpThreads, smem, s>>>(p, nullptr);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}

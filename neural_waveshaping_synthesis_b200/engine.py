@@ -172,6 +172,22 @@ class NwsEngine:
         """1 = tcgen05 harmonic mixer (default), 0 = fp32 SIMT mixer."""
         _lib.check(self.lib.nws_set_audio_impl(self.handle, impl))
 
+    def set_mlp_impl(self, impl: int):
+        """1 = tcgen05 MLP chain (default), 0 = fp32 SIMT layer kernels."""
+        _lib.check(self.lib.nws_set_mlp_impl(self.handle, impl))
+
+    def control_to_params(self, control: torch.Tensor):
+        """control [B,C,T] -> (film [B,256,T], bands [B,129,T])."""
+        control = _as_f32(control, self.device)
+        B, C, T = control.shape
+        film = torch.empty(B, 256, T, dtype=torch.float32, device=self.device)
+        bands = torch.empty(B, N_BANDS, T, dtype=torch.float32, device=self.device)
+        ws = self.workspace_for(B, T)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nws_stage_control_to_params(self.handle, _ptr(control), C, _ptr(film), _ptr(bands), B, T,
+                                                            _ptr(ws), ws.numel(), self._stream()))
+        return film, bands
+
     def set_profiling(self, enable: bool):
         _lib.check(self.lib.nws_set_profiling(self.handle, 1 if enable else 0))
 

@@ -88,6 +88,30 @@ def test_tcgen05_selftest():
         assert (D.double() - ref).abs().max().item() < 4e-6
 
 
+@pytest.mark.parametrize("impl", [1, 0])   # 1 = tcgen05 MLP chain (default), 0 = fp32 SIMT layers
+@pytest.mark.parametrize("tag", ["randinit", "vn"])
+def test_control_to_params(tag, impl, eng_rand, eng_vn):
+    """The whole hop-rate chain: control -> FiLM parameters and noise band gains."""
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    c = load_case("small_%s_newt" % tag)
+    eng.set_mlp_impl(impl)
+    try:
+        film, bands = eng.control_to_params(c["control"].cuda())
+        # a batch that spans several 128-frame tiles with a ragged tail
+        gen = torch.Generator().manual_seed(9)
+        big = torch.rand(3, 2, 171, generator=gen)
+        film_b, bands_b = eng.control_to_params(big.cuda())
+    finally:
+        eng.set_mlp_impl(1)
+    tol = 3e-5 if tag == "randinit" else 2e-3   # vn: the GRU's recurrent rounding dominates (see test_control_embedding)
+    assert err(film, c["part_film"])[0] < tol * max(1.0, float(c["part_film"].abs().max()))
+    assert err(bands, c["part_H"])[0] < tol * max(1.0, float(c["part_H"].abs().max()))
+    emb = oracle.control_module(w, big)
+    rf, rb = oracle.td_mlp(w, "newt.mlp", emb), oracle.td_mlp(w, "h_generator", emb)
+    assert err(film_b, rf)[0] < tol * max(1.0, float(rf.abs().max()))
+    assert err(bands_b, rb)[0] < tol * max(1.0, float(rb.abs().max()))
+
+
 @pytest.mark.parametrize("impl", [1, 0])   # 1 = tcgen05 harmonic mixer (default), 0 = fp32 SIMT mixer
 @pytest.mark.parametrize("tag", ["randinit", "vn"])
 def test_exciter_and_newt(tag, impl, eng_rand, eng_vn):
