@@ -3,6 +3,13 @@
 #pragma once
 #include "nws_internal.cuh"
 
+// Sine used inside the shaper MLP (1,600 evaluations per sample on the NEWT path): SFU-based, 2-term
+// reduction (arguments are a few tens of radians at most).  The LUT builder uses the accurate version so
+// FastNEWT tables match the reference's to 1 ulp-level (see nws_build_lut_kernel).
+#ifndef NWS_SHAPER_SIN
+#define NWS_SHAPER_SIN(x) (FAST ? nws_sinf_fast<2>(x) : nws_sinf(x))
+#endif
+
 struct NwsAudioParams {
   const float* f0;        // [B][T]
   const double* carry;    // [B][T]
@@ -28,6 +35,7 @@ struct NwsAudioParams {
 // ------------------------------------------------------------------------------------------------
 // One shaper's sine-MLP (TrainableNonlinearity.forward, shaping.py:36-37 with Sine, depth 4, width 8):
 // y = sin(w4 . sin(W3 sin(W2 sin(w1*(s*x) + b1) + b2) + b3) + b4).  `wp` = packed record (kShp* offsets).
+template <bool FAST>
 __device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, float x) {
   const float4 hd = *reinterpret_cast<const float4*>(wp);
   const float u = hd.x * x;
@@ -35,10 +43,10 @@ __device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, fl
   {
     const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW1), wb = *reinterpret_cast<const float4*>(wp + kShpW1 + 4);
     const float4 ba = *reinterpret_cast<const float4*>(wp + kShpB1), bb = *reinterpret_cast<const float4*>(wp + kShpB1 + 4);
-    h1[0] = nws_sinf(fmaf(wa.x, u, ba.x)); h1[1] = nws_sinf(fmaf(wa.y, u, ba.y));
-    h1[2] = nws_sinf(fmaf(wa.z, u, ba.z)); h1[3] = nws_sinf(fmaf(wa.w, u, ba.w));
-    h1[4] = nws_sinf(fmaf(wb.x, u, bb.x)); h1[5] = nws_sinf(fmaf(wb.y, u, bb.y));
-    h1[6] = nws_sinf(fmaf(wb.z, u, bb.z)); h1[7] = nws_sinf(fmaf(wb.w, u, bb.w));
+    h1[0] = NWS_SHAPER_SIN(fmaf(wa.x, u, ba.x)); h1[1] = NWS_SHAPER_SIN(fmaf(wa.y, u, ba.y));
+    h1[2] = NWS_SHAPER_SIN(fmaf(wa.z, u, ba.z)); h1[3] = NWS_SHAPER_SIN(fmaf(wa.w, u, ba.w));
+    h1[4] = NWS_SHAPER_SIN(fmaf(wb.x, u, bb.x)); h1[5] = NWS_SHAPER_SIN(fmaf(wb.y, u, bb.y));
+    h1[6] = NWS_SHAPER_SIN(fmaf(wb.z, u, bb.z)); h1[7] = NWS_SHAPER_SIN(fmaf(wb.w, u, bb.w));
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -46,7 +54,7 @@ __device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, fl
     float a = wp[kShpB2 + j];
     a = fmaf(wa.x, h1[0], a); a = fmaf(wa.y, h1[1], a); a = fmaf(wa.z, h1[2], a); a = fmaf(wa.w, h1[3], a);
     a = fmaf(wb.x, h1[4], a); a = fmaf(wb.y, h1[5], a); a = fmaf(wb.z, h1[6], a); a = fmaf(wb.w, h1[7], a);
-    h2[j] = nws_sinf(a);
+    h2[j] = NWS_SHAPER_SIN(a);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -54,12 +62,12 @@ __device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, fl
     float a = wp[kShpB3 + j];
     a = fmaf(wa.x, h2[0], a); a = fmaf(wa.y, h2[1], a); a = fmaf(wa.z, h2[2], a); a = fmaf(wa.w, h2[3], a);
     a = fmaf(wb.x, h2[4], a); a = fmaf(wb.y, h2[5], a); a = fmaf(wb.z, h2[6], a); a = fmaf(wb.w, h2[7], a);
-    h1[j] = nws_sinf(a);
+    h1[j] = NWS_SHAPER_SIN(a);
   }
   const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW4), wb = *reinterpret_cast<const float4*>(wp + kShpW4 + 4);
   float a = hd.y;
   a = fmaf(wa.x, h1[0], a); a = fmaf(wa.y, h1[1], a); a = fmaf(wa.z, h1[2], a); a = fmaf(wa.w, h1[3], a);
   a = fmaf(wb.x, h1[4], a); a = fmaf(wb.y, h1[5], a); a = fmaf(wb.z, h1[6], a); a = fmaf(wb.w, h1[7], a);
-  return nws_sinf(a);
+  return NWS_SHAPER_SIN(a);
 }
 

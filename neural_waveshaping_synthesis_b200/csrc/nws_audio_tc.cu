@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
           const float2 t2 = __ldg(row + (size_t)i * lut_size + (int)fl);
           y = NWS_ADD(NWS_MUL(t2.y, NWS_ADD(idx, -fl)), t2.x);
         } else {
-          y = nws_shaper_mlp(sm_shaper + c * kShaperStride, x);
+          y = nws_shaper_mlp<true>(sm_shaper + c * kShaperStride, x);
         }
         const float z = NWS_ADD(NWS_MUL(g_n, y), b_n);
         mix = fmaf(bw.y, z, mix);

@@ -77,3 +77,20 @@ extern "C" int nws_selftest_umma(const float* A, const float* B, float* D, int K
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }
+
+// Accuracy probe of the two device sine implementations (nws_math.h) on caller-chosen arguments.
+__global__ void nws_selftest_sin_kernel(const float* __restrict__ x, float* __restrict__ y_acc, float* __restrict__ y_fast3,
+                                        float* __restrict__ y_fast2, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y_acc[i] = nws_sinf(x[i]);
+  y_fast3[i] = nws_sinf_fast<3>(x[i]);
+  y_fast2[i] = nws_sinf_fast<2>(x[i]);
+}
+
+extern "C" int nws_selftest_sin(const float* x, float* y_acc, float* y_fast3, float* y_fast2, long long n, void* stream) {
+  if (!x || !y_acc || !y_fast3 || !y_fast2 || n < 1) { nws_set_error("nws_selftest_sin: bad argument"); return NWS_ERR_INVALID; }
+  nws_selftest_sin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y_acc, y_fast3, y_fast2, n);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}

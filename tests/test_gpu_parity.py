@@ -88,6 +88,27 @@ def test_tcgen05_selftest():
         assert (D.double() - ref).abs().max().item() < 4e-6
 
 
+def test_sin_variants():
+    """Device sine implementations of csrc/nws_math.h against float64: the polynomial version (oscillator
+    bank) and the SFU-based version (shaper MLP), over the argument ranges each one sees."""
+    from neural_waveshaping_synthesis_b200 import _lib
+    lib = _lib.load_library()
+    g = torch.Generator().manual_seed(0)
+    xs = torch.cat([(torch.rand(400000, generator=g) * 2 - 1) * 1.2e6, (torch.rand(400000, generator=g) * 2 - 1) * 2e5,
+                    (torch.rand(200000, generator=g) * 2 - 1) * 1300, (torch.rand(200000, generator=g) * 2 - 1) * 120,
+                    (torch.rand(200000, generator=g) * 2 - 1) * 4]).cuda()
+    ya, y3, y2 = torch.empty_like(xs), torch.empty_like(xs), torch.empty_like(xs)
+    assert lib.nws_selftest_sin(xs.data_ptr(), ya.data_ptr(), y3.data_ptr(), y2.data_ptr(), xs.numel(), None) == 0
+    ref = torch.sin(xs.double())
+    ea = (ya.double() - ref).abs().max().item()
+    e3 = (y3.double() - ref).abs().max().item()
+    small = xs.abs() < 1300
+    e2 = (y2.double() - ref)[small].abs().max().item()
+    print("sin max abs err: accurate %.3e  fast3 %.3e  fast2(|x|<1300) %.3e" % (ea, e3, e2))
+    assert ea < 1.5e-7
+    assert e3 < 6e-7 and e2 < 6e-7
+
+
 @pytest.mark.parametrize("impl", [1, 0])   # 1 = tcgen05 MLP chain (default), 0 = fp32 SIMT layers
 @pytest.mark.parametrize("tag", ["randinit", "vn"])
 def test_control_to_params(tag, impl, eng_rand, eng_vn):
