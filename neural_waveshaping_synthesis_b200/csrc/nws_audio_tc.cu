@@ -18,10 +18,22 @@
 #include "nws_audio_common.cuh"
 #include "nws_tc.cuh"
 
+// Oscillator sine: NWS_OSC_FAST=1 selects the SFU version (3.6e-7 max abs error on B200 instead of
+// 1.2e-7, ~10 fewer instructions per harmonic); the choice is made by measured end-to-end parity
+// (scripts/parity_report.py), see DESIGN.md.
+#ifndef NWS_OSC_FAST
+#define NWS_OSC_FAST 1
+#endif
+#if NWS_OSC_FAST
+#define NWS_OSC_SIN(x) nws_sinf_fast<3>(x)
+#else
+#define NWS_OSC_SIN(x) nws_sinf(x)
+#endif
+
 namespace {
 
-constexpr int kWgs = 4;                  // warpgroups per CTA
-constexpr int kTcThreads = kWgs * 128;
+constexpr int kWgs = 4;                  // compute warpgroups per CTA
+constexpr int kTcThreads = kWgs * 128 + kWgs * 32;   // + one MMA-issuing warp per compute warpgroup
 constexpr int kWBytes = kHarmPad * kShapers * 4;       // one tf32 part of the B operand (26,624 B)
 constexpr uint32_t kLboA = 16 * 128, kLboB = 8 * 128, kSbo = 128;
 
@@ -77,8 +89,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
                                                                      int* __restrict__ fault) {
   using C = TcCfg<USE_LUT>;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bars[kWgs][2];
-  __shared__ double warp_tot[kWgs][4];
+  __shared__ uint64_t fill_bar[kWgs][2];   // stage operand written (4 arrivals: one per compute warp)
+  __shared__ uint64_t free_bar[kWgs][2];   // the MMAs that read the stage have completed (tcgen05.commit)
+  __shared__ double warp_tot[kWgs + 1][4];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, lane = tid & 31, wwarp = wt >> 5;
@@ -86,10 +99,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   float* sm_small = reinterpret_cast<float*>(smem + C::oSmall);
   float2* sm_bw = reinterpret_cast<float2*>(sm_small);   // [64] (harmonic_mixer bias, mixdown weight)
   float* sm_shift = sm_small + 2 * kShapers;
-  float* sm_film = reinterpret_cast<float*>(smem + C::oFilm) + wg * 3 * kFilm;
-  float* sm_coef = reinterpret_cast<float*>(smem + C::oCoef) + wg * 2 * kShapers * 8;
+  float* sm_film = reinterpret_cast<float*>(smem + C::oFilm) + (wg & 3) * 3 * kFilm;
+  float* sm_coef = reinterpret_cast<float*>(smem + C::oCoef) + (wg & 3) * 2 * kShapers * 8;
   float* sm_shaper = reinterpret_cast<float*>(smem + C::oShaper);
-  unsigned char* a_base = smem + C::oA + wg * 4 * C::kStageBytes;   // [stage][hi|lo]
+  unsigned char* a_base = smem + C::oA + (wg & 3) * 4 * C::kStageBytes;   // [stage][hi|lo]
 
   // ---- CTA-lifetime staging
   for (int i = tid; i < 2 * kWBytes / 16; i += kTcThreads)
@@ -101,14 +114,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       reinterpret_cast<float4*>(sm_shaper)[i] = reinterpret_cast<const float4*>(p.shaper)[i];
   if (tid < 32) nws_tmem_alloc(&tmem_base_s, 64 * kWgs);
   if (tid == 0) {
-    for (int i = 0; i < kWgs * 2; ++i) nws_mbar_init(&bars[0][0] + i, 1);
+    for (int i = 0; i < kWgs * 2; ++i) {
+      nws_mbar_init(&fill_bar[0][0] + i, 4);
+      nws_mbar_init(&free_bar[0][0] + i, 1);
+    }
     nws_fence_mbar_init();
   }
   nws_fence_proxy_async();   // the weight tiles were written through the generic proxy
   nws_tc_fence_before();
   __syncthreads();
   nws_tc_fence_after();
-  const uint32_t tmem_acc = tmem_base_s + wg * 64;                       // this warpgroup's 64 columns
+  const uint32_t tmem_acc = tmem_base_s + (wg & 3) * 64;                 // this warpgroup's 64 columns
   const uint32_t tmem_lane = tmem_acc + ((uint32_t)(wwarp * 32) << 16);   // this warp's lane quarter
   const uint32_t idesc = nws_umma_idesc_tf32(128, 64);
   const uint32_t w_hi_addr = nws_smem_u32(smem + C::oW), w_lo_addr = w_hi_addr + kWBytes;
@@ -116,9 +132,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   const float mix_b = p.mix_b[0];
   const float inv_hop = (float)T / (float)N;
   const long long n_tiles = (long long)p.B * T;
-  uint32_t uses0 = 0, uses1 = 0;   // completed-or-pending commits per stage buffer (same in every thread)
+  uint32_t uses0 = 0, uses1 = 0;   // fills issued per stage buffer (same in every thread of the warpgroup)
   bool ok = true;
 
+  if (wg == kWgs) {
+    // ================= MMA warps: warp 16+w serves compute warpgroup w.  It sleeps on the stage's fill
+    // barrier (mbarrier.try_wait suspends in hardware), issues the 3xTF32 MMAs of the stage and commits to
+    // the stage's free barrier; the last stage's commit also tells the warpgroup its accumulator is complete.
+    const int w = wwarp;
+    if (lane == 0) {
+      uint32_t fills0 = 0, fills1 = 0;
+      const uint32_t a_wg = nws_smem_u32(smem + C::oA + w * 4 * C::kStageBytes);
+      const uint32_t acc = tmem_base_s + w * 64;
+      for (long long tile = (long long)blockIdx.x * kWgs + w; tile < n_tiles && ok; tile += (long long)gridDim.x * kWgs) {
+#pragma unroll 1
+        for (int st = 0; st < C::NST && ok; ++st) {
+          const int buf = st & 1;
+          ok = nws_mbar_wait(&fill_bar[w][buf], (buf ? fills1 : fills0) & 1);
+          if (!ok) break;
+          nws_tc_fence_after();
+          const int k0 = st * C::KS;
+          const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;
+          const uint32_t a_hi = a_wg + buf * 2 * C::kStageBytes, a_lo = a_hi + C::kStageBytes;
+          for (int j = 0; j < ks_here / 8; ++j) {
+            const uint64_t dah = nws_umma_smem_desc(a_hi + j * 2 * kLboA, kLboA, kSbo);
+            const uint64_t dal = nws_umma_smem_desc(a_lo + j * 2 * kLboA, kLboA, kSbo);
+            const uint32_t wb = (k0 / 4 + 2 * j) * kLboB;
+            const uint64_t dbh = nws_umma_smem_desc(w_hi_addr + wb, kLboB, kSbo);
+            const uint64_t dbl = nws_umma_smem_desc(w_lo_addr + wb, kLboB, kSbo);
+            nws_umma_tf32(acc, dah, dbh, idesc, (st | j) ? 1u : 0u);
+            nws_umma_tf32(acc, dal, dbh, idesc, 1u);
+            nws_umma_tf32(acc, dah, dbl, idesc, 1u);
+          }
+          nws_umma_commit(&free_bar[w][buf]);
+          if (buf) ++fills1; else ++fills0;
+        }
+      }
+    }
+  } else
   for (long long tile = (long long)blockIdx.x * kWgs + wg; tile < n_tiles; tile += (long long)gridDim.x * kWgs) {
     const int b = (int)(tile / T), t = (int)(tile - (long long)b * T);
     wg_barrier(wg);   // previous tile: film / warp_tot no longer read, TMEM loads done (fence below)
@@ -171,7 +222,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       const float k0f = (float)k0;
       const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;   // last stage may be short
       const uint32_t prior = buf ? uses1 : uses0;
-      if (prior > 0 && ok) ok = nws_mbar_wait(&bars[wg][buf], (prior - 1) & 1);   // MMAs that read this buffer are done
+      if (prior > 0 && ok) ok = nws_mbar_wait(&free_bar[wg][buf], (prior - 1) & 1);   // MMAs that read this buffer are done
       unsigned char* hi = a_base + buf * 2 * C::kStageBytes;
       unsigned char* lo = hi + C::kStageBytes;
 #pragma unroll
@@ -183,7 +234,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
             // harmonic number k = k0 + kk + j + 1 (k0f + const is exact: small integers).  Harmonics 102..104
             // are padding: their mixer weights are zero, so their (finite) sines are never seen.
             const float kf = k0f + (float)(kk + j + 1);
-            float s = nws_sinf(NWS_ADD(NWS_MUL(kf, phase), sm_shift[k0 + kk + j]));   // generators.py:60-61
+            float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL(kf, phase), sm_shift[k0 + kk + j]));   // generators.py:60-61
             s = NWS_MUL(f0u, kf) < 0.5f * kSampleRate ? s : 0.f;                       // generators.py:50-52
             h[j] = nws_tf32_hi(s);
             l[j] = nws_tf32_lo(s, h[j]);
@@ -193,30 +244,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
           *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
         }
       }
-      nws_fence_proxy_async();
-      nws_tc_fence_before();
-      wg_barrier(wg);
-      if (wt == 0) {
-        nws_tc_fence_after();
-        const uint32_t a_hi = a_addr + buf * 2 * C::kStageBytes, a_lo = a_hi + C::kStageBytes;
-        for (int j = 0; j < ks_here / 8; ++j) {
-          const uint64_t dah = nws_umma_smem_desc(a_hi + j * 2 * kLboA, kLboA, kSbo);
-          const uint64_t dal = nws_umma_smem_desc(a_lo + j * 2 * kLboA, kLboA, kSbo);
-          const uint32_t wb = (k0 / 4 + 2 * j) * kLboB;
-          const uint64_t dbh = nws_umma_smem_desc(w_hi_addr + wb, kLboB, kSbo);
-          const uint64_t dbl = nws_umma_smem_desc(w_lo_addr + wb, kLboB, kSbo);
-          nws_umma_tf32(tmem_acc, dah, dbh, idesc, (st | j) ? 1u : 0u);
-          nws_umma_tf32(tmem_acc, dal, dbh, idesc, 1u);
-          nws_umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
-        }
-        nws_umma_commit(&bars[wg][buf]);
+      nws_fence_proxy_async();   // operand stores -> visible to the tensor core's async proxy
+      nws_tc_fence_before();     // (first stage) this thread's TMEM reads of the previous tile are ordered too
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nws_smem_u32(&fill_bar[wg][buf])) : "memory");
       }
       if (buf) ++uses1; else ++uses0;
     }
     {  // accumulator complete when the last stage's commit lands (a commit covers all earlier MMAs)
       const int lb = (C::NST - 1) & 1;
       const uint32_t u = lb ? uses1 : uses0;
-      if (ok) ok = nws_mbar_wait(&bars[wg][lb], (u - 1) & 1);
+      if (ok) ok = nws_mbar_wait(&free_bar[wg][lb], (u - 1) & 1);
       nws_tc_fence_after();
     }
 

@@ -111,22 +111,39 @@ class NeuralWaveshaping(nn.Module):
                 sd["newt.shaping_fn." + k] = v
         return sd
 
+    def _weight_tensors(self):
+        """The 49 tensors of the C ABI's NwsTensor order, cached per (module-structure) so the per-call
+        change check is 49 (data_ptr, version) reads instead of a state_dict() walk."""
+        key = (id(self.newt), id(self.newt._modules.get("shaping_fn")), id(self.embedding), id(self.reverb))
+        cache = self.__dict__.get("_wt_cache")
+        if cache is None or cache[0] != key:
+            sd = self._state_for_engine()
+            cache = (key, sd, [sd[k] for k in _lib.TENSOR_KEYS])
+            object.__setattr__(self, "_wt_cache", cache)
+        return cache[1], cache[2]
+
     def _engine_for(self, like: torch.Tensor) -> NwsEngine:
         dev = like.device
         if dev.type != "cuda":
             raise RuntimeError("NeuralWaveshaping (B200) runs on CUDA only: inputs are on %s. There is no CPU "
                                "fallback; move the model and inputs with .to('cuda')." % dev)
-        for m in self.modules():
-            if isinstance(m, BoundToRoot) and (m._nws_root_ref is None or m._nws_root_ref() is not self):
-                m._bind_root(self)
         eng = self._engines.get(dev)
         if eng is None:
             eng = NwsEngine(dev)
             self._engines[dev] = eng
-        sd = self._state_for_engine()
-        sig = tuple((sd[k].data_ptr(), sd[k]._version) for k in _lib.TENSOR_KEYS)
+            for m in self.modules():
+                if isinstance(m, BoundToRoot):
+                    m._bind_root(self)
+        sd, tensors = self._weight_tensors()
+        if tensors[0].device != dev:   # the module was moved since the tensor list was cached
+            object.__setattr__(self, "_wt_cache", None)
+            sd, tensors = self._weight_tensors()
+        sig = tuple([(t.data_ptr(), t._version) for t in tensors])
         tag = self._loaded.get(dev)
         if tag is None or tag[0] != sig:
+            for m in self.modules():
+                if isinstance(m, BoundToRoot):
+                    m._bind_root(self)
             eng.load_weights(sd)
             tag = (sig, None)
         if isinstance(self.newt, FastNEWT):
