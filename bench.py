@@ -177,6 +177,19 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_traffic(variant):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/, written by scripts/ncu_summary.py); None if absent."""
+    path = os.path.join(REPO, "profiles", "r1_ncu_audio_tc_%s.json" % ("lut" if variant == "fastnewt" else "mlp"))
+    try:
+        d = json.load(open(path))[0]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+        return rd["value"] * scale[rd["unit"]] + wr["value"] * scale[wr["unit"]]
+    except Exception:
+        return None
+
+
 def workload_config(args):
     return {"workload": "%s forward, batch %d x %g s @ 16 kHz per GPU (BASELINE.json configs[%d])" %
             ("FastNEWT LUT" if args.variant == "fastnewt" else "NEWT MLP", args.batch_per_gpu, args.seconds,
@@ -312,9 +325,10 @@ def run_b200(args):
                 "h2d_bytes_per_step": B * 3 * T * 4, "d2h_bytes_per_step": B * N * 4},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "nws_audio_fused_kernel<%s>" % ("LUT" if args.variant == "fastnewt" else "MLP"),
+        "roofline": {"kernel": "nws_audio_tc_kernel<%s>" % ("LUT" if args.variant == "fastnewt" else "MLP"),
                      "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / hbm_peak) if achieved else None, "traffic": ncu_traffic(args.variant),
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": audio_ms,
                      "kernel_share_of_step": audio_ms / sum(stage_acc.values()) if stage_acc else None,
                      "fp32_issue": {"lane_ops_per_sample": ops_per_sample,

@@ -97,15 +97,15 @@ nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, c
     const float gh = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) + bh;
     const float gi = fmaf(wi1, x1, fmaf(wi0, x0, bi));
     if (r < 2 * kEmb) {
-      pre_rz[r] = gi + gh;
+      pre_rz[r] = nws_sigmoid(gi + gh);   // r and z gates: activated by the 256 threads that own their rows
     } else {
       pre_ni[r - 2 * kEmb] = gi;
       pre_nh[r - 2 * kEmb] = gh;
     }
     __syncthreads();
     if (r < kEmb) {
-      const float rg = nws_sigmoid(pre_rz[r]);
-      const float zg = nws_sigmoid(pre_rz[kEmb + r]);
+      const float rg = pre_rz[r];
+      const float zg = pre_rz[kEmb + r];
       const float ng = tanhf(fmaf(rg, pre_nh[r], pre_ni[r]));
       const float hn = fmaf(zg, h[r] - ng, ng);  // (1-z)*n + z*h
       h_s[(t + 1) & 1][r] = hn;

@@ -1,39 +1,74 @@
-// Radix-2 Stockham FFT on complex data in shared memory, shared by the noise branch (256-point
-// frames, generators.py:25-35) and the reverb (four-step FFT convolution, shaping.py:161-173).
+// Stockham autosort FFT on complex data in shared memory (radix-4 stages, one radix-2 stage when
+// log2 N is odd), shared by the noise branch (256-point frames, generators.py:25-35) and the reverb
+// (four-step FFT convolution, shaping.py:161-173).  Index math validated against numpy in
+// scripts/dev notes (mixed radix Stockham, Govindaraju et al. formulation).
 #pragma once
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ float2 nws_cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
+__device__ __forceinline__ float2 nws_cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 nws_csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-// `n_fft` independent FFTs of length N = 1 << log_n, element e of FFT f at buf[(e * n_fft + f)]
-// ("interleaved": consecutive threads work on consecutive FFTs -> conflict-free) when INTERLEAVED,
-// else at buf[f * N + e].  All threads of the CTA must call; ping-pongs between a and b and
-// returns the buffer holding the (natural-order) result.  tw[m] = exp(-2*pi*i*m/N), m < N/2
-// (tw_stride lets a longer master table be used).
+// tw[m * tw_stride] = exp(-2*pi*i*m/N) for m < N/2; the second half of the circle is -tw[m - N/2]
+template <bool INVERSE>
+__device__ __forceinline__ float2 nws_twiddle(const float2* __restrict__ tw, int tw_stride, int m, int half) {
+  float2 w = m < half ? tw[m * tw_stride] : tw[(m - half) * tw_stride];
+  if (m >= half) { w.x = -w.x; w.y = -w.y; }
+  if (INVERSE) w.y = -w.y;
+  return w;
+}
+
+// `n_fft` independent FFTs of length N = 1 << log_n.  Element e of FFT f lives at buf[e * n_fft + f] when
+// INTERLEAVED (consecutive threads -> consecutive FFTs: conflict-free for column transforms), else at
+// buf[f * N + e].  All threads of the CTA must call; ping-pongs between a and b and returns the buffer
+// holding the natural-order result.
 template <bool INVERSE, bool INTERLEAVED>
 __device__ __forceinline__ float2* nws_fft_smem(float2* a, float2* b, const float2* __restrict__ tw, int tw_stride,
                                                 int log_n, int n_fft, int tid, int n_threads) {
   const int N = 1 << log_n, half = N >> 1;
-  const int total = half * n_fft;
-  for (int s = 0; s < log_n; ++s) {
-    const int ns = 1 << s;
-    for (int q = tid; q < total; q += n_threads) {
-      int f, j;
-      if (INTERLEAVED) { f = q % n_fft; j = q / n_fft; } else { f = q / half; j = q - f * half; }
-      const int k = j & (ns - 1);
-      float2 w = tw[(k << (log_n - 1 - s)) * tw_stride];
-      if (INVERSE) w.y = -w.y;
-      const int i0 = INTERLEAVED ? j * n_fft + f : f * N + j;
-      const int i1 = INTERLEAVED ? (j + half) * n_fft + f : f * N + j + half;
-      const float2 v0 = a[i0];
-      const float2 v1 = nws_cmul(a[i1], w);
-      const int j0 = ((j >> s) << (s + 1)) + k;
-      const int o0 = INTERLEAVED ? j0 * n_fft + f : f * N + j0;
-      const int o1 = INTERLEAVED ? (j0 + ns) * n_fft + f : f * N + j0 + ns;
-      b[o0] = make_float2(v0.x + v1.x, v0.y + v1.y);
-      b[o1] = make_float2(v0.x - v1.x, v0.y - v1.y);
+  int ns = 1, s = 0;
+  while (s < log_n) {
+    if (log_n - s >= 2) {
+      const int T = N >> 2, total = T * n_fft;
+      const int tw_step = N / (4 * ns);
+      for (int q = tid; q < total; q += n_threads) {
+        int f, j;
+        if (INTERLEAVED) { f = q % n_fft; j = q / n_fft; } else { f = q / T; j = q - f * T; }
+        const int k = j & (ns - 1);
+        float2 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = a[INTERLEAVED ? (j + r * T) * n_fft + f : f * N + j + r * T];
+        if (k) {
+#pragma unroll
+          for (int r = 1; r < 4; ++r) v[r] = nws_cmul(v[r], nws_twiddle<INVERSE>(tw, tw_stride, r * k * tw_step, half));
+        }
+        const float2 a0 = nws_cadd(v[0], v[2]), a1 = nws_csub(v[0], v[2]), a2 = nws_cadd(v[1], v[3]);
+        const float2 d = nws_csub(v[1], v[3]);
+        const float2 a3 = INVERSE ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);  // * (+i) or * (-i)
+        const int j0 = ((j / ns) * ns << 2) + k;
+        float2 o[4] = {nws_cadd(a0, a2), nws_cadd(a1, a3), nws_csub(a0, a2), nws_csub(a1, a3)};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) b[INTERLEAVED ? (j0 + r * ns) * n_fft + f : f * N + j0 + r * ns] = o[r];
+      }
+      ns <<= 2;
+      s += 2;
+    } else {
+      const int total = half * n_fft;
+      for (int q = tid; q < total; q += n_threads) {
+        int f, j;
+        if (INTERLEAVED) { f = q % n_fft; j = q / n_fft; } else { f = q / half; j = q - f * half; }
+        const int k = j & (ns - 1);
+        const float2 w = nws_twiddle<INVERSE>(tw, tw_stride, k * (N / (2 * ns)), half);
+        const float2 v0 = a[INTERLEAVED ? j * n_fft + f : f * N + j];
+        const float2 v1 = nws_cmul(a[INTERLEAVED ? (j + half) * n_fft + f : f * N + j + half], w);
+        const int j0 = ((j / ns) * ns << 1) + k;
+        b[INTERLEAVED ? j0 * n_fft + f : f * N + j0] = nws_cadd(v0, v1);
+        b[INTERLEAVED ? (j0 + ns) * n_fft + f : f * N + j0 + ns] = nws_csub(v0, v1);
+      }
+      ns <<= 1;
+      s += 1;
     }
     __syncthreads();
     float2* t = a; a = b; b = t;
