@@ -225,23 +225,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       if (prior > 0 && ok) ok = nws_mbar_wait(&free_bar[wg][buf], (prior - 1) & 1);   // MMAs that read this buffer are done
       unsigned char* hi = a_base + buf * 2 * C::kStageBytes;
       unsigned char* lo = hi + C::kStageBytes;
+      // Anti-alias mask (generators.py:50-52): fp32(f0*k) < 8000 is monotone in k for f0 >= 0 and always true
+      // for f0 < 0, so one warp vote per stage classifies all 16 harmonics: every lane unmasked (no mask
+      // arithmetic), every lane masked (the operand is zero: no sines at all), or mixed (general path).
+      const float k_last = k0f + (float)ks_here, k_first = k0f + 1.0f;
+      const bool all_on = __all_sync(0xffffffffu, NWS_MUL(f0u, k_last) < 0.5f * kSampleRate && !(f0u != f0u));
+      const bool all_off = __all_sync(0xffffffffu, f0u >= 0.f && !(NWS_MUL(f0u, k_first) < 0.5f * kSampleRate));
+      if (all_off) {
 #pragma unroll
-      for (int kk = 0; kk < C::KS; kk += 4) {
-        if (kk < ks_here) {
-          float h[4], l[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            // harmonic number k = k0 + kk + j + 1 (k0f + const is exact: small integers).  Harmonics 102..104
-            // are padding: their mixer weights are zero, so their (finite) sines are never seen.
-            const float kf = k0f + (float)(kk + j + 1);
-            float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL(kf, phase), sm_shift[k0 + kk + j]));   // generators.py:60-61
-            s = NWS_MUL(f0u, kf) < 0.5f * kSampleRate ? s : 0.f;                       // generators.py:50-52
-            h[j] = nws_tf32_hi(s);
-            l[j] = nws_tf32_lo(s, h[j]);
+        for (int kk = 0; kk < C::KS; kk += 4) {
+          if (kk < ks_here) {
+            const uint32_t off = (kk >> 2) * kLboA + wt * 16;
+            *reinterpret_cast<float4*>(hi + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(lo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          const uint32_t off = (kk >> 2) * kLboA + wt * 16;   // chunk kk/4, row wt: conflict-free 16 B per thread
-          *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+      } else if (all_on) {
+#pragma unroll
+        for (int kk = 0; kk < C::KS; kk += 4) {
+          if (kk < ks_here) {
+            float h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // harmonic number k = k0 + kk + j + 1 (k0f + const is exact: small integers).  Harmonics 102..104
+              // are padding: their mixer weights are zero, so their (finite) sines are never seen.
+              const float kf = k0f + (float)(kk + j + 1);
+              const float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL(kf, phase), sm_shift[k0 + kk + j]));   // generators.py:60-61
+              h[j] = nws_tf32_hi(s);
+              l[j] = nws_tf32_lo(s, h[j]);
+            }
+            const uint32_t off = (kk >> 2) * kLboA + wt * 16;   // chunk kk/4, row wt: conflict-free 16 B per thread
+            *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < C::KS; kk += 4) {
+          if (kk < ks_here) {
+            float h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float kf = k0f + (float)(kk + j + 1);
+              float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL(kf, phase), sm_shift[k0 + kk + j]));
+              s = NWS_MUL(f0u, kf) < 0.5f * kSampleRate ? s : 0.f;
+              h[j] = nws_tf32_hi(s);
+              l[j] = nws_tf32_lo(s, h[j]);
+            }
+            const uint32_t off = (kk >> 2) * kLboA + wt * 16;
+            *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+          }
         }
       }
       nws_fence_proxy_async();   // operand stores -> visible to the tensor core's async proxy

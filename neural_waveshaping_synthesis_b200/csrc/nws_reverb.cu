@@ -39,18 +39,20 @@ __global__ void __launch_bounds__(256) nws_reverb_cols_fwd_kernel(const float* _
   for (int i = tid; i < n1 / 2; i += 256) tw_s[i] = tw_master[i * (kTwMaster / n1)];
   const float* xa = x + (size_t)(2 * pair) * N;
   const float* xb = 2 * pair + 1 < B ? x + (size_t)(2 * pair + 1) * N : nullptr;
+#pragma unroll 4
   for (int i = tid; i < n1 * W; i += 256) {
     const int r = i / W, c = i - r * W;
     const long long n = (long long)r * 256 + c0 + c;
-    a[i] = n < N ? make_float2(xa[n], xb ? xb[n] : 0.f) : make_float2(0.f, 0.f);
+    a[i] = n < N ? make_float2(__ldg(xa + n), xb ? __ldg(xb + n) : 0.f) : make_float2(0.f, 0.f);
   }
   __syncthreads();
   const float2* z = nws_fft_smem<false, true>(a, bb, tw_s, 1, log_n1, W, tid, 256);
   float2* dst = work + (size_t)pair * L;
+#pragma unroll 4
   for (int i = tid; i < n1 * W; i += 256) {
     const int k1 = i / W, c = i - k1 * W;
     const size_t idx = (size_t)k1 * 256 + c0 + c;
-    dst[idx] = nws_cmul(z[i], tw_big[idx]);
+    dst[idx] = nws_cmul(z[i], __ldg(tw_big + idx));
   }
 }
 
@@ -96,10 +98,11 @@ __global__ void __launch_bounds__(256) nws_reverb_cols_inv_kernel(float2* __rest
   const size_t L = (size_t)n1 * 256;
   float2* wk = work + (size_t)blockIdx.y * L;
   for (int i = tid; i < n1 / 2; i += 256) tw_s[i] = tw_master[i * (kTwMaster / n1)];
+#pragma unroll 4
   for (int i = tid; i < n1 * W; i += 256) {
     const int k1 = i / W, c = i - k1 * W;
     const size_t idx = (size_t)k1 * 256 + c0 + c;
-    float2 t = tw_big[idx];
+    float2 t = __ldg(tw_big + idx);
     t.y = -t.y;
     a[i] = nws_cmul(wk[idx], t);
   }
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(256) nws_reverb_fold_kernel(const float* __res
 static size_t cols_smem_bytes(int n1, int W) { return ((size_t)2 * n1 * W + n1 / 2) * sizeof(float2); }
 
 static int pick_cols(int n1) {
-  int W = 8192 / n1;  // 128 KB of ping-pong buffers
+  int W = 4096 / n1;  // 64 KB of ping-pong buffers: three CTAs per SM keep more loads in flight
   if (W > 16) W = 16;
   if (W < 1) W = 1;
   return W;
