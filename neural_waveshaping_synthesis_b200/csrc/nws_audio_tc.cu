@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       dst[0] = lo4;
       dst[1] = hi4;
     }
+    wg_barrier(wg);   // coefficient table visible to the whole warpgroup before the shaper loop reads it
 
     // ---- oscillator bank -> A operand stages -> tcgen05.mma
 #pragma unroll 1

@@ -303,6 +303,21 @@ def test_full_size_batch_properties():
     assert e[0] < TOL_CKPT_MAX and e[1] < TOL_CKPT_RMS, e
 
 
+def test_long_utterance_other_fft_plan():
+    """12 s utterances (T=1500, N=192000): another reverb transform length (L = 2^18), oscillator arguments up
+    to ~6e5 rad, phase carries deep into the fp64 scan — against the oracle."""
+    m, w = _model("vn", False)
+    f0, control = oracle.realistic_inputs(1500, w["data_mean"].numpy(), w["data_std"].numpy(), B=2)
+    f0 = f0.clone()
+    f0[1] *= 0.37
+    u, noise = oracle.draw_rng(1500, 11)
+    with torch.no_grad():
+        y = m(f0.cuda(), control.cuda(), phase_shift=u.reshape(-1).cuda(), noise=noise.cuda())
+    ref = oracle.forward(w, f0, control, u, noise)
+    e = err(y, ref)
+    assert e[0] < TOL_CKPT_MAX and e[1] < TOL_CKPT_RMS, e
+
+
 def test_device_rng_path_and_errors():
     m, w = _model("randinit", False)
     f0 = torch.rand(2, 1, 16).cuda()
