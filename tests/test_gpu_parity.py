@@ -348,3 +348,44 @@ def test_host_buffer_entry_point():
     y = m.synthesise_from_host(c["f0"].contiguous(), c["control"].contiguous(), out=out,
                                phase_shift=c["u_phase"].contiguous(), noise=c["noise"].contiguous())
     assert err(y, c["out"])[0] < TOL_RAND
+
+
+def test_c_abi_error_codes():
+    """Error behaviour at the C boundary (include/nws_b200.h): codes, messages, nothing launched."""
+    import ctypes
+    from neural_waveshaping_synthesis_b200 import _lib
+    from neural_waveshaping_synthesis_b200.engine import NwsEngine
+    lib = _lib.load_library()
+    w = load_weights("randinit")
+    eng = NwsEngine("cuda:0")
+    vp = ctypes.c_void_p
+    f0 = torch.rand(1, 1, 4, device="cuda")
+    control = torch.rand(1, 2, 4, device="cuda")
+    out = torch.empty(1, 512, device="cuda")
+    ws = torch.empty(1 << 24, dtype=torch.uint8, device="cuda")
+
+    def fwd(T=4, use_lut=0, ws_bytes=None, f0p=None):
+        return lib.nws_forward(eng.handle, vp(f0.data_ptr() if f0p is None else f0p), vp(control.data_ptr()), 2, None, None,
+                               1, 0, vp(out.data_ptr()), 1, T, use_lut, vp(ws.data_ptr()),
+                               ws.numel() if ws_bytes is None else ws_bytes, None)
+
+    assert fwd() == -3 and b"weights not loaded" in lib.nws_last_error()          # NWS_ERR_STATE
+    eng.load_weights({k: v for k, v in w.items() if not k.startswith("data_")})
+    assert fwd() == 0
+    assert fwd(T=1) == -1 and b"T must be >= 2" in lib.nws_last_error()            # NWS_ERR_INVALID, like the reference's T=1
+    assert fwd(use_lut=1) == -3 and b"lookup table" in lib.nws_last_error()        # FastNEWT without a table
+    assert fwd(ws_bytes=1024) == -5 and b"workspace too small" in lib.nws_last_error()
+    assert fwd(f0p=0) == -1
+    bad = _lib.NwsConfig()
+    lib.nws_default_config(ctypes.byref(bad))
+    bad.n_harmonics = 60
+    h = vp()
+    assert lib.nws_create(ctypes.byref(bad), ctypes.byref(h)) == -2                # NWS_ERR_UNSUPPORTED
+    tensors = (vp * _lib.N_TENSORS)(*[t.data_ptr() for t in eng._keep])
+    tensors[3] = None
+    assert lib.nws_load_weights(eng.handle, tensors, _lib.N_TENSORS, None) == -1
+    win = eng._keep[_lib.TENSOR_KEYS.index("noise_synth.window")].clone()
+    tensors = (vp * _lib.N_TENSORS)(*[t.data_ptr() for t in eng._keep])
+    tensors[_lib.TENSOR_KEYS.index("noise_synth.window")] = torch.ones_like(win).data_ptr()
+    assert lib.nws_load_weights(eng.handle, tensors, _lib.N_TENSORS, None) == -2   # not the periodic Hann window
+    torch.cuda.synchronize()
