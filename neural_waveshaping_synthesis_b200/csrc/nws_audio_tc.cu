@@ -183,6 +183,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     const int n = t * kHop + wt;
     const NwsLerp lc = nws_lerp_coords(n, T, inv_hop);
     const float* f0b = p.f0 + (size_t)b * T;
+    // issued early so their latency hides behind the scan / the whole tile: the hop's fp64 phase carry and the
+    // noise-branch sample that is added to the mixdown at the very end
+    const double carry_v = p.carry[(size_t)b * T + t];
+    const float noise_v = p.noise_in ? p.noise_in[(size_t)b * N + n] : 0.f;   // (aliases p.out: plain load)
     const float f0u = nws_lerp_apply(lc, f0b[lc.i0], f0b[lc.i1]);
     double v = (double)f0u;
 #pragma unroll
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     }
     if (lane == 31) warp_tot[wg][wwarp] = v;
     wg_barrier(wg);
-    double pre = p.carry[(size_t)b * T + t];
+    double pre = carry_v;
     for (int w = 0; w < wwarp; ++w) pre += warp_tot[wg][w];
     const float csum = (float)(pre + v);
     const float phase = nws_phase_from_cumsum(csum, (float)kSampleRate);
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     }
     nws_tc_fence_before();   // TMEM reads ordered before the next tile's first MMA (via the warpgroup barrier)
     float o = mix + mix_b;
-    if (p.noise_in) o += p.noise_in[(size_t)b * N + n];
+    o += noise_v;
     p.out[(size_t)b * N + n] = ok ? o : __int_as_float(0x7fc00000);
   }
   if (!ok && fault) atomicExch(fault, 1);
