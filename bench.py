@@ -190,6 +190,21 @@ def ncu_traffic(variant):
         return None
 
 
+def issue_view(variant):
+    """What actually bounds the fused kernel (it is neither HBM- nor tensor-bound): warp-instruction issue.
+    Figures from the committed ncu capture of this workload (profiles/)."""
+    path = os.path.join(REPO, "profiles", "r1_ncu_audio_tc_%s.json" % ("lut" if variant == "fastnewt" else "mlp"))
+    try:
+        d = json.load(open(path))[0]
+        g = lambda k: d[k]["value"]
+        return {"bound": "warp-instruction issue (fp32 SIMT epilogue + sine generation)",
+                "issue_slot_utilisation": g("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
+                "tensor_pipe_active": g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active") / 100.0,
+                "warp_instructions_per_launch": g("smsp__inst_executed.sum"), "source": os.path.basename(path)}
+    except Exception:
+        return {"bound": "warp-instruction issue", "source": None}
+
+
 def workload_config(args):
     return {"workload": "%s forward, batch %d x %g s @ 16 kHz per GPU (BASELINE.json configs[%d])" %
             ("FastNEWT LUT" if args.variant == "fastnewt" else "NEWT MLP", args.batch_per_gpu, args.seconds,
@@ -328,10 +343,6 @@ def run_b200(args):
     audio_ms = stage_acc.get("audio_fused", 0.0)
     algo_bytes = B * T * ALGO_BYTES_PER_UTT_FRAME          # 262,000 B per 4 s utterance
     achieved = algo_bytes / (audio_ms * 1e-3) / 1e9 if audio_ms > 0 else None
-    # fp32-issue view of the same kernel: FMA-class lane-ops per sample over the 128 lanes/clk/SM
-    ops_per_sample = 8.0e3 if args.variant == "fastnewt" else 17.0e3
-    sm_mhz = clocks.get("sm_mhz") or 1965.0
-    fma_peak = 148 * 128 * sm_mhz * 1e6
     line = {
         "metric": "audio samples/sec", "value": total_samples / (step_ms_max * 1e-3), "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max,
@@ -349,13 +360,10 @@ def run_b200(args):
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": audio_ms,
                      "kernel_share_of_step": audio_ms / sum(stage_acc.values()) if stage_acc else None,
-                     "fp32_issue": {"lane_ops_per_sample": ops_per_sample,
-                                    "achieved_frac_of_fma_issue": (ops_per_sample * B * N / (audio_ms * 1e-3)) / fma_peak
-                                    if audio_ms > 0 else None,
-                                    "note": "the fused kernel is fp32-issue bound, not HBM bound (SURVEY.md §8(d))"}},
+                     "issue_view": issue_view(args.variant)},
         "stages_ms": stage_acc,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only
         line["cpu_baseline"] = best_cpu_baseline(cpu_model, args, T)
     print(json.dumps(line))
     if dist is not None:

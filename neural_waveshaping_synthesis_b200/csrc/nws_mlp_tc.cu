@@ -217,34 +217,43 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
         const uint32_t drow = tmem_row + kColD + (n_blk & 1) * 128;
         const float* bias = vec_s + b * kVecStride;
         if (d.kind == 1) {
+          // the whole 128-channel row in registers: one burst of TMEM loads, then LayerNorm (dynamic.py:11-17)
+          // entirely in-thread with four independent accumulation chains
           const float* g = bias + 128;
           const float* be = bias + 256;
-          float sum = 0.f;
-#pragma unroll 1
-          for (int c0 = 0; c0 < kEmb; c0 += 16) {
-            float v[16];
-            nws_tmem_ld16(drow + c0, v);
+          float x[kEmb];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sum += v[i] + bias[c0 + i];
+          for (int c0 = 0; c0 < kEmb; c0 += 16) nws_tmem_ld16_nowait(drow + c0, x + c0);
+          nws_tmem_wait_ld();
+#pragma unroll
+          for (int c0 = 0; c0 < kEmb; c0 += 16) nws_reg_fence16(x + c0);
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int c = 0; c < kEmb; c += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias + c);
+            x[c] += bv.x; x[c + 1] += bv.y; x[c + 2] += bv.z; x[c + 3] += bv.w;
+            s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3];
           }
-          const float mean = sum * (1.0f / kEmb);
-          float q = 0.f;
-#pragma unroll 1
-          for (int c0 = 0; c0 < kEmb; c0 += 16) {
-            float v[16];
-            nws_tmem_ld16(drow + c0, v);
+          const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / kEmb);
+          float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { const float dd = (v[i] + bias[c0 + i]) - mean; q = fmaf(dd, dd, q); }
+          for (int c = 0; c < kEmb; c += 4) {
+            x[c] -= mean; x[c + 1] -= mean; x[c + 2] -= mean; x[c + 3] -= mean;
+            q0 = fmaf(x[c], x[c], q0); q1 = fmaf(x[c + 1], x[c + 1], q1);
+            q2 = fmaf(x[c + 2], x[c + 2], q2); q3 = fmaf(x[c + 3], x[c + 3], q3);
           }
-          const float rstd = 1.0f / sqrtf(q * (1.0f / kEmb) + 1e-5f);
-#pragma unroll 1
-          for (int c0 = 0; c0 < kEmb; c0 += 16) {
-            float v[16], y[16];
-            nws_tmem_ld16(drow + c0, v);
+          const float rstd = 1.0f / sqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / kEmb) + 1e-5f);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float t = fmaf(((v[i] + bias[c0 + i]) - mean) * rstd, g[c0 + i], be[c0 + i]);
-              y[i] = t > 0.f ? t : 0.01f * t;
+          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+            float y[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 gv = *reinterpret_cast<const float4*>(g + c0 + i);
+              const float4 bv = *reinterpret_cast<const float4*>(be + c0 + i);
+              const float t0 = fmaf(x[c0 + i] * rstd, gv.x, bv.x), t1 = fmaf(x[c0 + i + 1] * rstd, gv.y, bv.y);
+              const float t2 = fmaf(x[c0 + i + 2] * rstd, gv.z, bv.z), t3 = fmaf(x[c0 + i + 3] * rstd, gv.w, bv.w);
+              y[i] = t0 > 0.f ? t0 : 0.01f * t0; y[i + 1] = t1 > 0.f ? t1 : 0.01f * t1;
+              y[i + 2] = t2 > 0.f ? t2 : 0.01f * t2; y[i + 3] = t3 > 0.f ? t3 : 0.01f * t3;
             }
             store_a16(tmem_row, c0, y);
           }
@@ -252,13 +261,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
           nws_tc_fence_before();
           mbar_arrive(&a_ready);
         } else if (d.kind == 0) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < kEmb; c0 += 16) {
-            float v[16];
-            nws_tmem_ld16(drow + c0, v);
+          float x[kEmb];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += bias[c0 + i];
-            store_a16(tmem_row, c0, v);
+          for (int c0 = 0; c0 < kEmb; c0 += 16) nws_tmem_ld16_nowait(drow + c0, x + c0);
+          nws_tmem_wait_ld();
+#pragma unroll
+          for (int c0 = 0; c0 < kEmb; c0 += 16) nws_reg_fence16(x + c0);
+#pragma unroll
+          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[c0 + i] += bias[c0 + i];
+            store_a16(tmem_row, c0, x + c0);
           }
           tmem_wait_st();
           nws_tc_fence_before();
