@@ -56,26 +56,29 @@ int nws_launch_phase_carry(const float* f0, double* carry, int B, int T, cudaStr
 
 // ------------------------------------------------------------------------------------------------
 // GRU(2 -> 128), h0 = 0, gate order r,z,n (neural_waveshaping.py:21,25).
-// One CTA per utterance, one thread per gate row: the thread keeps its W_hh row (128 floats) in
-// registers for all T steps, h lives in shared memory.  The recurrence is the only sequential
-// dependency at hop rate; 384 threads x 128 FMAs per step.
+// One CTA per utterance, 384 threads = one per gate row; the recurrence is the only sequential dependency at
+// hop rate.  A warp owns 32 rows.  The dot products W_hh[row] . h are computed K-SPLIT across the warp: lane l
+// holds the four columns k = 4l..4l+3 of all 32 rows of its warp in registers (128 floats, for all T steps),
+// reads only its own four h values per step (one conflict-free LDS.128 per warp instead of 32 broadcast
+// loads), forms 32 four-term partial sums and the warp combines them with a reduce-scatter of xor-shuffles.
+// Register j of lane l accumulates row (j ^ l): with that swizzle every exchange stage is
+// `v[j] += shfl_xor(v[j | o], o)` with static register indices and no selects, and lane l ends up with the
+// complete dot product of row l.
 __device__ __forceinline__ float nws_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __global__ void __launch_bounds__(kGates, 1)
 nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, const float* __restrict__ b_ih,
                const float* __restrict__ b_hh, const float* __restrict__ control, int ctrl_channels,
                float* __restrict__ hbuf, int T) {
-  const int b = blockIdx.x, r = threadIdx.x;
+  const int b = blockIdx.x, r = threadIdx.x, lane = r & 31, row0 = r & ~31;
   __shared__ __align__(16) float h_s[2][kEmb];
   __shared__ float pre_rz[2 * kEmb];
   __shared__ float pre_ni[kEmb], pre_nh[kEmb];
 
-  float w[kEmb];
+  float4 w[32];
 #pragma unroll
-  for (int k = 0; k < kEmb; k += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(w_hh + (size_t)r * kEmb + k);
-    w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
-  }
+  for (int j = 0; j < 32; ++j)
+    w[j] = *reinterpret_cast<const float4*>(w_hh + (size_t)(row0 + (j ^ lane)) * kEmb + 4 * lane);
   const float wi0 = w_ih[r * 2], wi1 = w_ih[r * 2 + 1], bi = b_ih[r], bh = b_hh[r];
   const float* c0 = control + (size_t)b * ctrl_channels * T;
   const float* c1 = c0 + T;
@@ -86,15 +89,21 @@ nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, c
   for (int t = 0; t < T; ++t) {
     const float* h = h_s[t & 1];
     const float nx0 = t + 1 < T ? c0[t + 1] : 0.0f, nx1 = t + 1 < T ? c1[t + 1] : 0.0f;  // prefetch
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+    const float4 hv = *reinterpret_cast<const float4*>(h + 4 * lane);
+    float v[16];
 #pragma unroll
-    for (int k = 0; k < kEmb; k += 8) {
-      const float4 p = *reinterpret_cast<const float4*>(h + k);
-      const float4 q = *reinterpret_cast<const float4*>(h + k + 4);
-      a0 = fmaf(w[k], p.x, a0); a1 = fmaf(w[k + 1], p.y, a1); a2 = fmaf(w[k + 2], p.z, a2); a3 = fmaf(w[k + 3], p.w, a3);
-      a4 = fmaf(w[k + 4], q.x, a4); a5 = fmaf(w[k + 5], q.y, a5); a6 = fmaf(w[k + 6], q.z, a6); a7 = fmaf(w[k + 7], q.w, a7);
+    for (int j = 0; j < 16; ++j) {
+      const float a = fmaf(w[j].w, hv.w, fmaf(w[j].z, hv.z, fmaf(w[j].y, hv.y, w[j].x * hv.x)));
+      const float c = fmaf(w[j | 16].w, hv.w, fmaf(w[j | 16].z, hv.z, fmaf(w[j | 16].y, hv.y, w[j | 16].x * hv.x)));
+      v[j] = a + __shfl_xor_sync(0xffffffffu, c, 16);
     }
-    const float gh = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) + bh;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j | 8], 8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j | 4], 4);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j | 2], 2);
+    const float gh = (v[0] + __shfl_xor_sync(0xffffffffu, v[1], 1)) + bh;   // full dot product of row r
     const float gi = fmaf(wi1, x1, fmaf(wi0, x0, bi));
     if (r < 2 * kEmb) {
       pre_rz[r] = nws_sigmoid(gi + gh);   // r and z gates: activated by the 256 threads that own their rows
