@@ -10,25 +10,35 @@
 // carry[b][t] = sum over hops t' < t of sum_{n in hop t'} double(f0_up[n])   (generators.py:59:
 // torch's CPU cumsum accumulates float32 inputs in double and rounds each output to float32; the
 // audio kernel adds the in-hop fp64 prefix to this carry and rounds once).
-__global__ void __launch_bounds__(128) nws_phase_carry_kernel(const float* __restrict__ f0, double* __restrict__ carry,
-                                                              int T) {
+constexpr int kCarryThreads = 512;
+
+__global__ void __launch_bounds__(kCarryThreads) nws_phase_carry_kernel(const float* __restrict__ f0,
+                                                                        double* __restrict__ carry, int T) {
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* f = f0 + (size_t)b * T;
   const float inv_hop = (float)T / (float)(T * kHop);
-  __shared__ double warp_tot[4];
+  __shared__ double warp_tot[kCarryThreads / 32];
   __shared__ double chunk_tot;
   double base = 0.0;
-  for (int t0 = 0; t0 < T; t0 += 128) {
+  for (int t0 = 0; t0 < T; t0 += kCarryThreads) {
     const int t = t0 + tid;
     double s = 0.0;
     if (t < T) {
       const float fm = f[t > 0 ? t - 1 : 0], fc = f[t], fp = f[t + 1 < T ? t + 1 : T - 1];
-      for (int r = 0; r < kHop; ++r) {
-        const NwsLerp c = nws_lerp_coords(t * kHop + r, T, inv_hop);
-        const float x0 = c.i0 == t ? fc : (c.i0 < t ? fm : fp);
-        const float x1 = c.i1 == t ? fc : (c.i1 < t ? fm : fp);
-        s += (double)nws_lerp_apply(c, x0, x1);
+      // four independent fp64 chains over the hop's 128 samples (exact for audio-range f0)
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int r = 0; r < kHop; r += 4) {
+        double q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const NwsLerp c = nws_lerp_coords(t * kHop + r + u, T, inv_hop);
+          const float x0 = c.i0 == t ? fc : (c.i0 < t ? fm : fp);
+          const float x1 = c.i1 == t ? fc : (c.i1 < t ? fm : fp);
+          q[u] = (double)nws_lerp_apply(c, x0, x1);
+        }
+        s0 += q[0]; s1 += q[1]; s2 += q[2]; s3 += q[3];
       }
+      s = (s0 + s1) + (s2 + s3);
     }
     double v = s;  // inclusive warp scan
 #pragma unroll
@@ -41,7 +51,7 @@ __global__ void __launch_bounds__(128) nws_phase_carry_kernel(const float* __res
     double pre = 0.0;
     for (int w = 0; w < warp; ++w) pre += warp_tot[w];
     if (t < T) carry[(size_t)b * T + t] = base + pre + (v - s);
-    if (tid == 127) chunk_tot = pre + v;
+    if (tid == kCarryThreads - 1) chunk_tot = pre + v;
     __syncthreads();
     base += chunk_tot;
     __syncthreads();
@@ -49,7 +59,7 @@ __global__ void __launch_bounds__(128) nws_phase_carry_kernel(const float* __res
 }
 
 int nws_launch_phase_carry(const float* f0, double* carry, int B, int T, cudaStream_t s) {
-  nws_phase_carry_kernel<<<B, 128, 0, s>>>(f0, carry, T);
+  nws_phase_carry_kernel<<<B, kCarryThreads, 0, s>>>(f0, carry, T);
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }

@@ -86,17 +86,22 @@ __global__ void __launch_bounds__(256) nws_reverb_rows_kernel(float2* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------- R3
+// FUSE_FOLD (possible when the circular length Lc is a multiple of 256, i.e. the wrapped sample n + Lc sits in
+// the same column, Lc/256 rows further down, inside this CTA's shared memory): the wrap, the dry add and the
+// final store happen here and the time-domain work array is never written or re-read.
+template <bool FUSE_FOLD>
 __global__ void __launch_bounds__(256) nws_reverb_cols_inv_kernel(float2* __restrict__ work,
                                                                   const float2* __restrict__ tw_big,
                                                                   const float2* __restrict__ tw_master, int n1,
-                                                                  int log_n1, int W) {
+                                                                  int log_n1, int W, const float* __restrict__ x,
+                                                                  float* __restrict__ out, int B, int N, int Lc) {
   extern __shared__ __align__(16) float2 smem2[];
   float2* a = smem2;
   float2* bb = smem2 + n1 * W;
   float2* tw_s = smem2 + 2 * n1 * W;
-  const int tid = threadIdx.x, c0 = blockIdx.x * W;
+  const int tid = threadIdx.x, c0 = blockIdx.x * W, pair = blockIdx.y;
   const size_t L = (size_t)n1 * 256;
-  float2* wk = work + (size_t)blockIdx.y * L;
+  float2* wk = work + (size_t)pair * L;
   for (int i = tid; i < n1 / 2; i += 256) tw_s[i] = tw_master[i * (kTwMaster / n1)];
 #pragma unroll 4
   for (int i = tid; i < n1 * W; i += 256) {
@@ -109,10 +114,29 @@ __global__ void __launch_bounds__(256) nws_reverb_cols_inv_kernel(float2* __rest
   __syncthreads();
   const float2* z = nws_fft_smem<true, true>(a, bb, tw_s, 1, log_n1, W, tid, 256);
   const float scale = 1.0f / (float)L;
-  for (int i = tid; i < n1 * W; i += 256) {
-    const int r = i / W, c = i - r * W;
-    const float2 v = z[i];
-    wk[(size_t)r * 256 + c0 + c] = make_float2(v.x * scale, v.y * scale);
+  if (FUSE_FOLD) {
+    // out[b][n] = x[b][n] + y[n] + y[n + Lc], y = linear convolution (zero beyond N + 31998)
+    const int rows = (N + 255) / 256, shift = Lc / 256;
+    const long long ylen = (long long)N + kReverbIr - 1;
+    const int b0 = 2 * pair, b1 = 2 * pair + 1;
+    for (int i = tid; i < rows * W; i += 256) {
+      const int r = i / W, c = i - r * W;
+      const long long n = (long long)r * 256 + c0 + c;
+      if (n >= N) continue;
+      float2 v = z[i];
+      if (n + Lc < ylen) {   // r + shift < n1 always holds here: n + Lc < N + 32000 <= L
+        const float2 u = z[(r + shift) * W + c];
+        v.x += u.x; v.y += u.y;
+      }
+      out[(size_t)b0 * N + n] = x[(size_t)b0 * N + n] + v.x * scale;
+      if (b1 < B) out[(size_t)b1 * N + n] = x[(size_t)b1 * N + n] + v.y * scale;
+    }
+  } else {
+    for (int i = tid; i < n1 * W; i += 256) {
+      const int r = i / W, c = i - r * W;
+      const float2 v = z[i];
+      wk[(size_t)r * 256 + c0 + c] = make_float2(v.x * scale, v.y * scale);
+    }
   }
 }
 
@@ -208,7 +232,8 @@ int nws_reverb_get_plan(NwsContext* ctx, int fft_len, cudaStream_t s, NwsReverbP
     NWS_CUDA_OK(e);
     const size_t smem = cols_smem_bytes(n1, pl->cols_per_cta);
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_reverb_cols_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_reverb_cols_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_reverb_cols_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_reverb_cols_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     (void)smem;
     ++ctx->n_plans;
   }
@@ -235,11 +260,18 @@ int nws_launch_reverb(NwsContext* ctx, const float* x, float* out, float2* work,
   if (rc) return rc;
   nws_reverb_rows_kernel<<<dim3(pl->n1 / 2, n_pairs), 256, 0, s>>>(work, pl->ir_spec, ctx->tw_master, pl->n1, 0);
   NWS_LAUNCH_CHECK();
-  nws_reverb_cols_inv_kernel<<<dim3(256 / W, n_pairs), 256, cols_smem_bytes(pl->n1, W), s>>>(
-      work, pl->tw_big, ctx->tw_master, pl->n1, pl->log_n1, W);
-  NWS_LAUNCH_CHECK();
   const int Lc = N > kReverbIr ? N : kReverbIr;
-  nws_reverb_fold_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, work, out, B, N, (size_t)L, Lc);
-  NWS_LAUNCH_CHECK();
+  if (Lc % 256 == 0) {
+    // (x + y*scale: the scale is applied to the sum y[n] + y[n+Lc] — same value up to one rounding)
+    nws_reverb_cols_inv_kernel<true><<<dim3(256 / W, n_pairs), 256, cols_smem_bytes(pl->n1, W), s>>>(
+        work, pl->tw_big, ctx->tw_master, pl->n1, pl->log_n1, W, x, out, B, N, Lc);
+    NWS_LAUNCH_CHECK();
+  } else {
+    nws_reverb_cols_inv_kernel<false><<<dim3(256 / W, n_pairs), 256, cols_smem_bytes(pl->n1, W), s>>>(
+        work, pl->tw_big, ctx->tw_master, pl->n1, pl->log_n1, W, x, out, B, N, Lc);
+    NWS_LAUNCH_CHECK();
+    nws_reverb_fold_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, work, out, B, N, (size_t)L, Lc);
+    NWS_LAUNCH_CHECK();
+  }
   return NWS_OK;
 }
