@@ -92,6 +92,28 @@ extern "C" int nws_load_weights(NwsHandle ctx, const float* const* tensors, int 
       return NWS_ERR_UNSUPPORTED;
     }
   }
+  {
+    // argument bound of the shaper MLP's inner sines (layers 2-4 see sines in [-1,1] as inputs)
+    static const int kW[3] = {NWS_T_SHAPER_W2, NWS_T_SHAPER_W3, NWS_T_SHAPER_W4};
+    static const int kB[3] = {NWS_T_SHAPER_B2, NWS_T_SHAPER_B3, NWS_T_SHAPER_B4};
+    static const int kRows[3] = {kShapers * 8, kShapers * 8, kShapers};
+    float* hw = (float*)malloc((size_t)kShapers * 8 * 9 * sizeof(float));
+    if (!hw) { nws_set_error("nws_load_weights: out of host memory"); return NWS_ERR_CUDA; }
+    float bound = 0.f;
+    for (int l = 0; l < 3; ++l) {
+      cudaError_t e = cudaMemcpyAsync(hw, tensors[kW[l]], (size_t)kRows[l] * 8 * sizeof(float), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(hw + kRows[l] * 8, tensors[kB[l]], (size_t)kRows[l] * sizeof(float), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) { free(hw); nws_set_error("nws_load_weights: %s", cudaGetErrorString(e)); return NWS_ERR_CUDA; }
+      for (int r = 0; r < kRows[l]; ++r) {
+        float a = fabsf(hw[kRows[l] * 8 + r]);
+        for (int i = 0; i < 8; ++i) a += fabsf(hw[r * 8 + i]);
+        if (!(a <= bound)) bound = a;   // NaN-propagating max
+      }
+    }
+    free(hw);
+    ctx->shaper_inner_bound = bound;
+  }
   int rc = nws_launch_pack_weights(ctx, tensors, s);
   if (rc) return rc;
   rc = nws_launch_mlp_tc_pack(ctx, tensors, s);

@@ -112,7 +112,7 @@ __global__ void nws_build_lut_kernel(const float* __restrict__ shaper, const flo
   const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= table_size) return;
   const float x = points ? points[i] : nws_linspace_value(i, table_size, tmin, tmax);
-  lut[(size_t)c * table_size + i] = nws_shaper_mlp<false>(shaper + c * kShaperStride, x);
+  lut[(size_t)c * table_size + i] = nws_shaper_mlp<0>(shaper + c * kShaperStride, x);
 }
 
 // (T[i], T[min(i+1,size-1)] - T[i]): the difference is the same fp32 subtraction FastNEWT.shaping_fn
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kAudioThreads, USE_LUT ? 3 : 2) nws_audio_fuse
         const float* row = p.lut + (size_t)c * p.lut_size;
         y = nws_lut_lerp(__ldg(row + li.lower), __ldg(row + li.upper), li.fract);
       } else {
-        y = nws_shaper_mlp<true>(sm + kSmShaper + c * kShaperStride, x);
+        y = nws_shaper_mlp<1>(sm + kSmShaper + c * kShaperStride, x);
       }
       const float z = NWS_ADD(NWS_MUL(g_n, y), b_n);
       mix = fmaf(sm[kSmMixW + c], z, mix);

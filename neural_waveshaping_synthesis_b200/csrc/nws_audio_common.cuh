@@ -6,9 +6,13 @@
 // Sine used inside the shaper MLP (1,600 evaluations per sample on the NEWT path): SFU-based, 2-term
 // reduction (arguments are a few tens of radians at most).  The LUT builder uses the accurate version so
 // FastNEWT tables match the reference's to 1 ulp-level (see nws_build_lut_kernel).
-#ifndef NWS_SHAPER_SIN
-#define NWS_SHAPER_SIN(x) (FAST ? nws_sinf_fast<2>(x) : nws_sinf(x))
-#endif
+// MODE 0: polynomial sine everywhere (LUT builder).  MODE 1: SFU sine with 2-term reduction everywhere.
+// MODE 2: as 1 for the first layer (its argument scales with the input), and bare sin.approx for layers 2-4,
+// whose arguments are bounded by max_j(|b_j| + sum_i |W_ji|) because the previous layer's outputs are sines —
+// the bound is checked when the weights are loaded (nws_load_weights) and MODE 2 is used only if it is <= 8
+// (3.8 at most in the shipped checkpoints), where x/2pi keeps the error at the SFU's own 4e-7 level.
+#define NWS_SHAPER_SIN(x) (MODE == 0 ? nws_sinf(x) : nws_sinf_fast<2>(x))
+#define NWS_SHAPER_SIN_INNER(x) (MODE == 0 ? nws_sinf(x) : (MODE == 1 ? nws_sinf_fast<2>(x) : __sinf(x)))
 
 struct NwsAudioParams {
   const float* f0;        // [B][T]
@@ -35,7 +39,7 @@ struct NwsAudioParams {
 // ------------------------------------------------------------------------------------------------
 // One shaper's sine-MLP (TrainableNonlinearity.forward, shaping.py:36-37 with Sine, depth 4, width 8):
 // y = sin(w4 . sin(W3 sin(W2 sin(w1*(s*x) + b1) + b2) + b3) + b4).  `wp` = packed record (kShp* offsets).
-template <bool FAST>
+template <int MODE>
 __device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, float x) {
   const float4 hd = *reinterpret_cast<const float4*>(wp);
   const float u = hd.x * x;
@@ -54,7 +58,7 @@ __device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, fl
     float a = wp[kShpB2 + j];
     a = fmaf(wa.x, h1[0], a); a = fmaf(wa.y, h1[1], a); a = fmaf(wa.z, h1[2], a); a = fmaf(wa.w, h1[3], a);
     a = fmaf(wb.x, h1[4], a); a = fmaf(wb.y, h1[5], a); a = fmaf(wb.z, h1[6], a); a = fmaf(wb.w, h1[7], a);
-    h2[j] = NWS_SHAPER_SIN(a);
+    h2[j] = NWS_SHAPER_SIN_INNER(a);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -62,12 +66,12 @@ __device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, fl
     float a = wp[kShpB3 + j];
     a = fmaf(wa.x, h2[0], a); a = fmaf(wa.y, h2[1], a); a = fmaf(wa.z, h2[2], a); a = fmaf(wa.w, h2[3], a);
     a = fmaf(wb.x, h2[4], a); a = fmaf(wb.y, h2[5], a); a = fmaf(wb.z, h2[6], a); a = fmaf(wb.w, h2[7], a);
-    h1[j] = NWS_SHAPER_SIN(a);
+    h1[j] = NWS_SHAPER_SIN_INNER(a);
   }
   const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW4), wb = *reinterpret_cast<const float4*>(wp + kShpW4 + 4);
   float a = hd.y;
   a = fmaf(wa.x, h1[0], a); a = fmaf(wa.y, h1[1], a); a = fmaf(wa.z, h1[2], a); a = fmaf(wa.w, h1[3], a);
   a = fmaf(wb.x, h1[4], a); a = fmaf(wb.y, h1[5], a); a = fmaf(wb.z, h1[6], a); a = fmaf(wb.w, h1[7], a);
-  return NWS_SHAPER_SIN(a);
+  return NWS_SHAPER_SIN_INNER(a);
 }
 

@@ -84,7 +84,7 @@ __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <bool USE_LUT, bool TAP>
+template <bool USE_LUT, bool TAP, int MLP_MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAudioParams p, const float* __restrict__ w_umma,
                                                                      int* __restrict__ fault) {
   using C = TcCfg<USE_LUT>;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
           const float2 t2 = __ldg(row + (size_t)i * lut_size + (int)fl);
           y = NWS_ADD(NWS_MUL(t2.y, NWS_ADD(idx, -fl)), t2.x);
         } else {
-          y = nws_shaper_mlp<true>(sm_shaper + c * kShaperStride, x);
+          y = nws_shaper_mlp<MLP_MODE>(sm_shaper + c * kShaperStride, x);
         }
         const float z = NWS_ADD(NWS_MUL(g_n, y), b_n);
         mix = fmaf(bw.y, z, mix);
@@ -363,20 +363,25 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
 
   static bool attr_done = false;
   if (!attr_done) {
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
     attr_done = true;
   }
   const long long tiles = (long long)B * T;
   const long long want = (tiles + kWgs - 1) / kWgs;
   const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
   const float* wu = w + ctx->lay.hmix_umma;
-  if (use_lut && !exciter_out) nws_audio_tc_kernel<true, false><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
-  else if (use_lut) nws_audio_tc_kernel<true, true><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
-  else if (!exciter_out) nws_audio_tc_kernel<false, false><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
-  else nws_audio_tc_kernel<false, true><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
+  const bool direct = ctx->shaper_inner_bound <= 8.0f;   // see NWS_SHAPER_SIN_INNER
+  if (use_lut && !exciter_out) nws_audio_tc_kernel<true, false, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
+  else if (use_lut) nws_audio_tc_kernel<true, true, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
+  else if (!exciter_out && direct) nws_audio_tc_kernel<false, false, 2><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
+  else if (!exciter_out) nws_audio_tc_kernel<false, false, 1><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
+  else if (direct) nws_audio_tc_kernel<false, true, 2><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
+  else nws_audio_tc_kernel<false, true, 1><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }

@@ -107,6 +107,7 @@ struct NwsContext {
   int mlp_impl = 1;            // 1 = tcgen05 MLP chain (nws_mlp_tc.cu), 0 = fp32 SIMT layers (nws_encoder.cu)
   float* mlp_tc = nullptr;     // TC weight blob (hi/lo parts, canonical UMMA layout, chunked)
   int mlp_tc_off[11] = {};
+  float shaper_inner_bound = 1e30f;   // max_j(|b_j| + sum_i |W_ji|) over shaper layers 2-4 (set by nws_load_weights)
   int audio_impl = 1;          // 1 = tcgen05 harmonic mixer (nws_audio_tc.cu), 0 = fp32 SIMT (nws_audio.cu)
   int device = 0;
   // optional per-stage timing of nws_forward (cudaEvents on the launch stream)
