@@ -277,12 +277,11 @@ int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry
   p.lut_span_rcp = 1.0f / p.lut_span;
   p.noise_in = noise_in; p.out = out; p.exciter_out = exciter_out; p.B = B; p.T = T;
 
-  static bool attr_done = false;
+  static bool attr_done[64] = {};
   const size_t sm_lut = kSmFloatsLut * sizeof(float), sm_mlp = kSmFloatsMlp * sizeof(float);
-  if (!attr_done) {
+  if (nws_first_use_on_device(attr_done)) {
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lut));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mlp));
-    attr_done = true;
   }
   const long long tiles = (long long)B * T;
   const int per_sm = use_lut ? 3 : 2;

@@ -361,15 +361,14 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   p.lut_span_rcp = 1.0f / p.lut_span;
   p.noise_in = noise_in; p.out = out; p.exciter_out = exciter_out; p.B = B; p.T = T;
 
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (nws_first_use_on_device(attr_done)) {
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
-    attr_done = true;
   }
   const long long tiles = (long long)B * T;
   const long long want = (tiles + kWgs - 1) / kWgs;

@@ -247,11 +247,10 @@ nws_linear128_kernel(const float* __restrict__ X, const float* __restrict__ Wt, 
 int nws_launch_linear(const float* X, const float* Wt, const float* bias, const float* ln_g, const float* ln_b,
                       float* Y, int M, int n_out, int ldw, int ldy, bool ln_act, cudaStream_t s) {
   const size_t smem = (size_t)(kEmb * kEmb + kLinFrames * kLinXs) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (nws_first_use_on_device(attr_done)) {
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_linear128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_linear128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
   }
   dim3 grid((M + kLinFrames - 1) / kLinFrames, (ldy + 127) / 128);
   if (ln_act) {

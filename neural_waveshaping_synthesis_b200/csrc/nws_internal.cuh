@@ -143,6 +143,16 @@ int nws_reverb_fft_len(int N);  // L = n1*256 >= N + kReverbIr - 1, n1 a power o
 void nws_set_error(const char* fmt, ...);
 extern thread_local uint64_t g_nws_launches;
 
+// cudaFuncSetAttribute is per device: "first use" flags are kept per device ordinal (a process may drive
+// several GPUs through several handles).
+inline bool nws_first_use_on_device(bool* flags) {
+  int d = 0;
+  cudaGetDevice(&d);
+  if (flags[d & 63]) return false;
+  flags[d & 63] = true;
+  return true;
+}
+
 #define NWS_CUDA_OK(expr)                                                                   \
   do {                                                                                      \
     cudaError_t _e = (expr);                                                                \

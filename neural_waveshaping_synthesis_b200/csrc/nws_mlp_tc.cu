@@ -390,11 +390,10 @@ int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, flo
   p.blk[10].bias = L.mlp[1].b_out; p.blk[11].bias = L.mlp[1].b_out + 128;
   p.packed = ctx->packed; p.w_tc = ctx->mlp_tc; p.h = hbuf; p.film = film; p.bands = bands; p.M = M;
 
-  static bool attr_done = false;
+  static bool attr_done[64] = {};
   const int smem = kSlots * kSlotBytes;
-  if (!attr_done) {
+  if (nws_first_use_on_device(attr_done)) {
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
   }
   const int tiles = (M + 127) / 128;
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;

@@ -389,3 +389,24 @@ def test_c_abi_error_codes():
     tensors[_lib.TENSOR_KEYS.index("noise_synth.window")] = torch.ones_like(win).data_ptr()
     assert lib.nws_load_weights(eng.handle, tensors, _lib.N_TENSORS, None) == -2   # not the periodic Hann window
     torch.cuda.synchronize()
+
+
+def test_cuda_graph_capture_and_replay():
+    """The forward enqueues kernels only (no host synchronisation, no allocation in the C library after the
+    first call of a shape), so it can be captured in a CUDA graph and replayed — bit-identical to eager."""
+    m, w = _model("randinit", True)
+    c = load_case("small_randinit_fast")
+    f0, control = c["f0"].cuda(), c["control"].cuda()
+    u, noise = c["u_phase"].cuda(), c["noise"].cuda()
+    with torch.no_grad():
+        eager = m(f0, control, phase_shift=u, noise=noise).clone()   # warm-up: plans, workspace, weights
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = m(f0, control, phase_shift=u, noise=noise)
+        for _ in range(3):
+            y.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(y, eager)
+    assert err(y, c["out"])[0] < TOL_RAND
