@@ -45,6 +45,7 @@ struct MlpTcParams {
   float* film;            // [M][256]
   float* bands;           // [M][132]
   int M;
+  int split;              // 1: even CTAs run blocks 0-5 (proj + FiLM chain), odd CTAs blocks 6-11 (proj + noise chain) of a tile
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -100,6 +101,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
   __shared__ __align__(16) float vec_s[kBlocks * kVecStride];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (p.M + 127) / 128;
+  // work items: a tile, or (split) half of a tile's block sequence — the two halves are self-contained
+  const int item0 = p.split ? blockIdx.x >> 1 : blockIdx.x, item_step = p.split ? gridDim.x >> 1 : gridDim.x;
+  const int b_begin = p.split ? (blockIdx.x & 1) * 6 : 0, b_end = p.split ? b_begin + 6 : kBlocks;
   for (int i = tid; i < kBlocks * kVecStride; i += kMlpThreads) {
     const int b = i / kVecStride, r = i % kVecStride, which = r >> 7, c = r & 127;
     const MlpBlockDesc& d = p.blk[b];
@@ -128,8 +132,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
     if (lane == 0) {
       uint32_t n_fill = 0;   // chunks issued so far (slot = n_fill % kSlots)
       bool ok = true;
-      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-        for (int b = 0; b < kBlocks && ok; ++b) {
+      for (int tile = item0; tile < n_tiles && ok; tile += item_step) {
+        for (int b = b_begin; b < b_end && ok; ++b) {
           const MlpBlockDesc d = p.blk[b];
           const uint32_t chunk_bytes = 2u * d.n * kChunkK * 4u;
           for (int ck = 0; ck < kEmb / kChunkK && ok; ++ck, ++n_fill) {
@@ -149,8 +153,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
     if (lane == 0) {
       uint32_t n_use = 0, a_ver = 0, n_blk = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-        for (int b = 0; b < kBlocks && ok; ++b, ++n_blk) {
+      for (int tile = item0; tile < n_tiles && ok; tile += item_step) {
+        for (int b = b_begin; b < b_end && ok; ++b, ++n_blk) {
           const MlpBlockDesc d = p.blk[b];
           if (d.new_a) {   // wait for the epilogue warpgroup to publish this block's A
             ok = nws_mbar_wait(&a_ready, a_ver & 1);
@@ -188,11 +192,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
     const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t n_blk = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+    for (int tile = item0; tile < n_tiles && ok; tile += item_step) {
       const int row = tile * 128 + tid;
       const bool valid = row < p.M;
       const float* hrow = p.h + (size_t)(valid ? row : 0) * kEmb;
-      for (int b = 0; b < kBlocks && ok; ++b, ++n_blk) {
+      for (int b = b_begin; b < b_end && ok; ++b, ++n_blk) {
         const MlpBlockDesc d = p.blk[b];
         if (b == 0 || b == 6) {
           // A <- this frame's GRU state (the embedding projection's input), hi/lo split
@@ -396,7 +400,8 @@ int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, flo
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   const int tiles = (M + 127) / 128;
-  const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  p.split = 2 * tiles <= ctx->sm_count ? 1 : 0;   // few tiles: halve the dependent-block chain per CTA (latency)
+  const int grid = p.split ? 2 * tiles : (tiles < ctx->sm_count ? tiles : ctx->sm_count);
   nws_mlp_tc_kernel<<<grid, kMlpThreads, smem, s>>>(p, nullptr);
   NWS_LAUNCH_CHECK();
   return NWS_OK;
