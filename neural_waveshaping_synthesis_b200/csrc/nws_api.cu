@@ -194,6 +194,7 @@ NwsWorkspace nws_carve_workspace(void* base, int B, int T, int fft_len) {
   w.xspec = (float2*)take((size_t)T * kBandsPad * sizeof(float2));
   w.dry = (float*)take((size_t)B * N * sizeof(float));
   w.scratch = (float*)take(M * kFilm * sizeof(float));
+  w.counters = (int*)take(16 * sizeof(int));
   w.rev = (float2*)take((size_t)((B + 1) / 2) * fft_len * sizeof(float2));
   w.total = off;
   return w;
@@ -240,8 +241,9 @@ static int check_common(NwsContext* ctx, int B, int T, void* ws, size_t ws_bytes
 
 static int launch_audio(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
-                        int use_lut, cudaStream_t s) {
-  return ctx->audio_impl ? nws_launch_audio_tc(ctx, f0, carry, film, u_phase, noise_in, out, exciter_out, B, T, use_lut, s)
+                        int* tile_counter, int use_lut, cudaStream_t s) {
+  return ctx->audio_impl ? nws_launch_audio_tc(ctx, f0, carry, film, u_phase, noise_in, out, exciter_out, B, T, 0, T,
+                                               tile_counter, use_lut, s)
                          : nws_launch_audio(ctx, f0, carry, film, u_phase, noise_in, out, exciter_out, B, T, use_lut, s);
 }
 
@@ -333,7 +335,7 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   NWS_STAGE(ctx, kStNoiseSpec, s, nws_launch_noise_spectrum(ctx, noise, w.xspec, T, s));
   NWS_STAGE(ctx, kStNoiseFilter, s, nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, s));
   // fused audio-rate kernel: dry = newt(exciter) + noise
-  NWS_STAGE(ctx, kStAudio, s, launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, use_lut, s));
+  NWS_STAGE(ctx, kStAudio, s, launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, w.counters, use_lut, s));
   // reverb
   NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb(ctx, w.dry, out, w.rev, B, N, s));
   return NWS_OK;
@@ -410,7 +412,7 @@ extern "C" int nws_stage_audio(NwsHandle ctx, const float* f0, const float* film
   cudaStream_t s = (cudaStream_t)stream;
   NWS_TRY(nws_launch_bct_to_rows(film, w.film, B, kFilm, T, kFilm, s));
   NWS_TRY(nws_launch_phase_carry(f0, w.carry, B, T, s));
-  return launch_audio(ctx, f0, w.carry, w.film, u_phase, nullptr, newt_out, exciter_out, B, T, use_lut, s);
+  return launch_audio(ctx, f0, w.carry, w.film, u_phase, nullptr, newt_out, exciter_out, B, T, w.counters, use_lut, s);
 }
 
 extern "C" int nws_stage_noise(NwsHandle ctx, const float* H, const float* noise, float* out, int B, int T,

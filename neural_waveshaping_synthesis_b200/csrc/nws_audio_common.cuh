@@ -33,6 +33,8 @@ struct NwsAudioParams {
   float* out;             // [B][N]
   float* exciter_out;     // [B][64][N] or null
   int B, T;
+  int t_begin, t_end;     // hop range [t_begin, t_end) rendered by this launch (whole utterance: 0, T)
+  int* tile_counter;      // device int, zero at launch: dynamic tile scheduler of nws_audio_tc_kernel
 };
 
 

@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   __shared__ uint64_t free_bar[kWgs][2];   // the MMAs that read the stage have completed (tcgen05.commit)
   __shared__ double warp_tot[kWgs + 1][4];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int tile_s[kWgs];              // tile handed to each warpgroup by the dynamic scheduler
+  __shared__ volatile int done_s[kWgs];     // warpgroup has run out of tiles (tells its MMA warp to stop)
 
   const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, lane = tid & 31, wwarp = wt >> 5;
   const int T = p.T, N = T * kHop;
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   if (!USE_LUT)
     for (int i = tid; i < kShapers * kShaperStride / 4; i += kTcThreads)
       reinterpret_cast<float4*>(sm_shaper)[i] = reinterpret_cast<const float4*>(p.shaper)[i];
+  if (tid < kWgs) done_s[tid] = 0;
   if (tid < 32) nws_tmem_alloc(&tmem_base_s, 64 * kWgs);
   if (tid == 0) {
     for (int i = 0; i < kWgs * 2; ++i) {
@@ -131,7 +134,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   const uint32_t a_addr = nws_smem_u32(a_base);
   const float mix_b = p.mix_b[0];
   const float inv_hop = (float)T / (float)N;
-  const long long n_tiles = (long long)p.B * T;
+  const int hops = p.t_end - p.t_begin;
+  const long long n_tiles = (long long)p.B * hops;
   uint32_t uses0 = 0, uses1 = 0;   // fills issued per stage buffer (same in every thread of the warpgroup)
   bool ok = true;
 
@@ -144,12 +148,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       uint32_t fills0 = 0, fills1 = 0;
       const uint32_t a_wg = nws_smem_u32(smem + C::oA + w * 4 * C::kStageBytes);
       const uint32_t acc = tmem_base_s + w * 64;
-      for (long long tile = (long long)blockIdx.x * kWgs + w; tile < n_tiles && ok; tile += (long long)gridDim.x * kWgs) {
+      bool more = true;
+      while (more && ok) {   // one iteration per tile of warpgroup w; tiles are handed out dynamically
 #pragma unroll 1
         for (int st = 0; st < C::NST && ok; ++st) {
           const int buf = st & 1;
-          ok = nws_mbar_wait(&fill_bar[w][buf], (buf ? fills1 : fills0) & 1);
-          if (!ok) break;
+          const uint32_t par = (buf ? fills1 : fills0) & 1;
+          uint32_t spins = 0;
+          while (!nws_mbar_try_wait(&fill_bar[w][buf], par)) {
+            if (st == 0 && done_s[w]) { more = false; break; }   // the warpgroup found no further tile
+            if (++spins > (1u << 26)) { ok = false; break; }
+          }
+          if (!more || !ok) break;
           nws_tc_fence_after();
           const int k0 = st * C::KS;
           const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;
@@ -170,9 +180,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       }
     }
   } else
-  for (long long tile = (long long)blockIdx.x * kWgs + wg; tile < n_tiles; tile += (long long)gridDim.x * kWgs) {
-    const int b = (int)(tile / T), t = (int)(tile - (long long)b * T);
-    wg_barrier(wg);   // previous tile: film / warp_tot no longer read, TMEM loads done (fence below)
+  {
+  // dynamic tile scheduler: tiles (utterance b, hop t) are claimed from a global counter, so CTAs that start
+  // late (SMs still busy with the encoder of a later time block) do not hold tiles hostage
+  if (wt == 0) tile_s[wg] = atomicAdd(p.tile_counter, 1);
+  int next_tile = 0;
+  for (;;) {
+    wg_barrier(wg);   // previous tile: film / coefficient table / warp_tot no longer read; tile_s published
+    const long long tile = tile_s[wg];
+    if (tile >= n_tiles) break;
+    if (wt == 0) next_tile = atomicAdd(p.tile_counter, 1);   // claimed now, needed a whole tile later
+    const int b = (int)(tile / hops), t = p.t_begin + (int)(tile - (long long)b * hops);
     for (int i = wt; i < 3 * kFilm / 4; i += 128) {
       const int slot = i / (kFilm / 4), fr = t - 1 + slot;
       if (fr >= 0 && fr < T)
@@ -339,6 +357,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     float o = mix + mix_b;
     o += noise_v;
     p.out[(size_t)b * N + n] = ok ? o : __int_as_float(0x7fc00000);
+    if (wt == 0) tile_s[wg] = next_tile;   // ordered before the readers by the barrier at the top of the loop
+  }
+  if (wt == 0) done_s[wg] = 1;
   }
   if (!ok && fault) atomicExch(fault, 1);
   nws_tc_fence_before();
@@ -350,7 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
 
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
-                        int use_lut, cudaStream_t s) {
+                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s) {
   NwsAudioParams p{};
   const float* w = ctx->packed;
   p.f0 = f0; p.carry = carry; p.film = film; p.u_phase = u_phase;
@@ -360,6 +381,8 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   p.lut_span = ctx->lut_max - ctx->lut_min;
   p.lut_span_rcp = 1.0f / p.lut_span;
   p.noise_in = noise_in; p.out = out; p.exciter_out = exciter_out; p.B = B; p.T = T;
+  p.t_begin = t_begin; p.t_end = t_end; p.tile_counter = tile_counter;
+  NWS_CUDA_OK(cudaMemsetAsync(tile_counter, 0, sizeof(int), s));
 
   static bool attr_done[64] = {};
   if (nws_first_use_on_device(attr_done)) {
@@ -370,7 +393,7 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
   }
-  const long long tiles = (long long)B * T;
+  const long long tiles = (long long)B * (t_end - t_begin);
   const long long want = (tiles + kWgs - 1) / kWgs;
   const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
   const float* wu = w + ctx->lay.hmix_umma;

@@ -132,6 +132,7 @@ struct NwsWorkspace {
   float2* xspec;      // [T][kBandsPad]
   float* dry;         // [B][N]
   float* scratch;     // [M][256]  layout conversion for the stage entry points
+  int* counters;      // [16] tile counters of the dynamic schedulers
   float2* rev;        // [ceil(B/2)][L]
   size_t total;
 };
@@ -189,7 +190,7 @@ int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry
                      int use_lut, cudaStream_t s);
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
-                        int use_lut, cudaStream_t s);
+                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s);
 size_t nws_mlp_tc_blob_floats();
 int nws_launch_mlp_tc_pack(NwsContext* ctx, const float* const* tensors, cudaStream_t s);
 int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, cudaStream_t s);
