@@ -185,6 +185,11 @@ int nws_get_stage_times(NwsHandle handle, float* ms_out, int n);
  * h_generator (neural_waveshaping.py:69-72,78,82; shaping.py:68) — the whole hop-rate chain. */
 int nws_stage_control_to_params(NwsHandle handle, const float* control, int ctrl_channels, float* film_out,
                                 float* bands_out, int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+/* Pipelined forward (default on): the GRU runs in 128-frame time blocks on an internal stream while the
+ * caller's stream renders the blocks already encoded (MLP chain, noise hops, audio hops); used when the
+ * batch is large enough (B*T >= 4096, T >= 129).  0 = strictly serial kernels on the caller's stream. */
+int nws_set_pipeline(NwsHandle handle, int enable);
+
 /* Implementation of the hop-rate MLP chain: 1 (default) = one tcgen05 kernel, activations in TMEM, weights
  * streamed by cp.async.bulk (csrc/nws_mlp_tc.cu); 0 = fp32 SIMT layer kernels (csrc/nws_encoder.cu). */
 int nws_set_mlp_impl(NwsHandle handle, int impl);

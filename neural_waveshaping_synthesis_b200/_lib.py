@@ -96,6 +96,8 @@ def load_library():
         L.nws_stage_reverb.argtypes = [vp, vp, vp, c_int, c_int, vp, c_size_t, vp]
         L.nws_selftest_sin.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, vp]
         L.nws_selftest_sin.restype = c_int
+        L.nws_set_pipeline.argtypes = [vp, c_int]
+        L.nws_set_pipeline.restype = c_int
         L.nws_set_mlp_impl.argtypes = [vp, c_int]
         L.nws_set_mlp_impl.restype = c_int
         L.nws_stage_control_to_params.argtypes = [vp, vp, c_int, vp, vp, c_int, c_int, vp, c_size_t, vp]
@@ -129,7 +131,7 @@ EXPORTED_SYMBOLS = [
     "nws_build_lut", "nws_set_lut", "nws_get_lut", "nws_workspace_bytes", "nws_forward", "nws_forward_host",
     "nws_stage_control_embedding", "nws_stage_td_mlp", "nws_stage_audio", "nws_stage_lut_lookup", "nws_stage_noise", "nws_stage_reverb",
     "nws_reverb_workspace_bytes", "nws_shaper_eval_scratch_bytes", "nws_shaper_eval", "nws_launch_count",
-    "nws_set_profiling", "nws_get_stage_times", "nws_selftest_umma", "nws_set_audio_impl", "nws_set_mlp_impl", "nws_stage_control_to_params", "nws_selftest_sin",
+    "nws_set_profiling", "nws_get_stage_times", "nws_selftest_umma", "nws_set_audio_impl", "nws_set_mlp_impl", "nws_stage_control_to_params", "nws_selftest_sin", "nws_set_pipeline",
 ]
 STAGE_NAMES = ["rng", "phase_carry", "gru", "proj", "film_mlp", "noise_mlp", "noise_spectrum", "noise_filter",
                "audio_fused", "reverb"]

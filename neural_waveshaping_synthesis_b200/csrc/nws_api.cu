@@ -57,6 +57,11 @@ extern "C" int nws_create(const NwsConfig* cfg, NwsHandle* out) {
   }
   int rc = nws_make_twiddle_master(ctx);
   if (rc) { cudaFree(ctx->packed); delete ctx; return rc; }
+  // internal encoder stream + fork/join events of the pipelined forward (timing disabled: cheaper)
+  e = cudaStreamCreateWithFlags(&ctx->enc_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  for (int i = 0; i < kMaxTimeBlocks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_block[i], cudaEventDisableTiming);
+  if (e != cudaSuccess) { nws_set_error("nws_create: %s", cudaGetErrorString(e)); nws_destroy(ctx); return NWS_ERR_CUDA; }
   *out = ctx;
   return NWS_OK;
 }
@@ -66,6 +71,10 @@ extern "C" int nws_destroy(NwsHandle ctx) {
   nws_reverb_free_plans(ctx);
   for (int i = 0; i < 2 * kStCount; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->enc_stream) { cudaStreamSynchronize(ctx->enc_stream); cudaStreamDestroy(ctx->enc_stream); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < kMaxTimeBlocks; ++i)
+    if (ctx->ev_block[i]) cudaEventDestroy(ctx->ev_block[i]);
   cudaFree(ctx->packed);
   cudaFree(ctx->mlp_tc);
   cudaFree(ctx->lut);
@@ -194,7 +203,8 @@ NwsWorkspace nws_carve_workspace(void* base, int B, int T, int fft_len) {
   w.xspec = (float2*)take((size_t)T * kBandsPad * sizeof(float2));
   w.dry = (float*)take((size_t)B * N * sizeof(float));
   w.scratch = (float*)take(M * kFilm * sizeof(float));
-  w.counters = (int*)take(16 * sizeof(int));
+  w.counters = (int*)take(kMaxTimeBlocks * sizeof(int));
+  w.h_state = (float*)take((size_t)B * kEmb * sizeof(float));
   w.rev = (float2*)take((size_t)((B + 1) / 2) * fft_len * sizeof(float2));
   w.total = off;
   return w;
@@ -263,9 +273,9 @@ extern "C" int nws_stage_control_to_params(NwsHandle ctx, const float* control, 
   if (!control || !film_out || !bands_out || ctrl_channels < 2) { nws_set_error("nws_stage_control_to_params: bad argument"); return NWS_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   const int M = B * T;
-  NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, s));
+  NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, T, nullptr, s));
   if (ctx->mlp_impl) {
-    NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, s));
+    NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, 0, T, s));
   } else {
     NWS_TRY(nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b, nullptr, nullptr,
                               w.emb, M, kEmb, kEmb, kEmb, false, s));
@@ -321,23 +331,59 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   }
   // hop rate: phase carries, control encoder, FiLM parameters, noise band gains
   NWS_STAGE(ctx, kStCarry, s, nws_launch_phase_carry(f0, w.carry, B, T, s));
-  NWS_STAGE(ctx, kStGru, s, nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, s));
-  if (ctx->mlp_impl) {
-    // projection + both TimeDistributedMLPs in one tensor-core kernel (activations stay in TMEM)
-    NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, s));
-  } else {
-    NWS_STAGE(ctx, kStProj, s, nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b,
-                                                 nullptr, nullptr, w.emb, M, kEmb, kEmb, kEmb, false, s));
-    NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_td_mlp(ctx, NWS_MLP_FILM, w.emb, w.act0, w.act1, w.film, M, s));
-    NWS_STAGE(ctx, kStMlpNoise, s, nws_launch_td_mlp(ctx, NWS_MLP_NOISE, w.emb, w.act0, w.act1, w.bands, M, s));
-  }
-  // noise branch -> dry
   NWS_STAGE(ctx, kStNoiseSpec, s, nws_launch_noise_spectrum(ctx, noise, w.xspec, T, s));
-  NWS_STAGE(ctx, kStNoiseFilter, s, nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, s));
-  // fused audio-rate kernel: dry = newt(exciter) + noise
-  NWS_STAGE(ctx, kStAudio, s, launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, w.counters, use_lut, s));
+
+  const int n_blocks = (T + 127) / 128;
+  const bool pipelined = ctx->pipeline && ctx->mlp_impl && ctx->audio_impl && !ctx->profile && ctx->enc_stream &&
+                         n_blocks >= 2 && n_blocks <= kMaxTimeBlocks && (long long)B * T >= 4096;
+  if (pipelined) {
+    // The GRU is 500 dependent steps on B SMs; everything downstream only needs the frames already encoded.
+    // So the recurrence runs in 128-frame time blocks on an internal stream, and the main stream renders
+    // block j (MLP chain -> noise hops -> audio hops) as soon as block j is encoded, on the SMs the GRU does
+    // not occupy (the audio kernel claims its tiles dynamically).  Stream/event dependencies only.
+    cudaStream_t g = ctx->enc_stream;
+    NWS_CUDA_OK(cudaEventRecord(ctx->ev_fork, s));
+    NWS_CUDA_OK(cudaStreamWaitEvent(g, ctx->ev_fork, 0));
+    for (int j = 0; j < n_blocks; ++j) {
+      const int t0 = j * 128, t1 = t0 + 128 < T ? t0 + 128 : T;
+      NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, t0, t1, w.h_state, g));
+      NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[j], g));
+    }
+    for (int j = 0; j < n_blocks; ++j) {
+      const int t0 = j * 128, t1 = t0 + 128 < T ? t0 + 128 : T;
+      NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[j], 0));
+      NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, t0, t1, s));
+      NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, t0, t1, s));
+      // hop t interpolates FiLM frames t-1..t+1: the block's audio lags one hop, the last block catches up
+      const int a0 = t0 > 0 ? t0 - 1 : 0, a1 = j + 1 < n_blocks ? t1 - 1 : T;
+      if (a1 > a0)
+        NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, a0, a1,
+                                    w.counters + j, use_lut, s));
+    }
+  } else {
+    NWS_STAGE(ctx, kStGru, s, nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, T, nullptr, s));
+    if (ctx->mlp_impl) {
+      // projection + both TimeDistributedMLPs in one tensor-core kernel (activations stay in TMEM)
+      NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, 0, T, s));
+    } else {
+      NWS_STAGE(ctx, kStProj, s, nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b,
+                                                   nullptr, nullptr, w.emb, M, kEmb, kEmb, kEmb, false, s));
+      NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_td_mlp(ctx, NWS_MLP_FILM, w.emb, w.act0, w.act1, w.film, M, s));
+      NWS_STAGE(ctx, kStMlpNoise, s, nws_launch_td_mlp(ctx, NWS_MLP_NOISE, w.emb, w.act0, w.act1, w.bands, M, s));
+    }
+    // noise branch -> dry
+    NWS_STAGE(ctx, kStNoiseFilter, s, nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, 0, T, s));
+    // fused audio-rate kernel: dry = newt(exciter) + noise
+    NWS_STAGE(ctx, kStAudio, s, launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, w.counters, use_lut, s));
+  }
   // reverb
   NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb(ctx, w.dry, out, w.rev, B, N, s));
+  return NWS_OK;
+}
+
+extern "C" int nws_set_pipeline(NwsHandle ctx, int enable) {
+  if (!ctx) { nws_set_error("nws_set_pipeline: NULL handle"); return NWS_ERR_INVALID; }
+  ctx->pipeline = enable != 0;
   return NWS_OK;
 }
 
@@ -383,7 +429,7 @@ extern "C" int nws_stage_control_embedding(NwsHandle ctx, const float* control, 
   NWS_TRY(check_common(ctx, B, T, workspace, workspace_bytes, "nws_stage_control_embedding", &w));
   if (!control || !emb || ctrl_channels < 2) { nws_set_error("nws_stage_control_embedding: bad argument"); return NWS_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
-  NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, s));
+  NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, T, nullptr, s));
   NWS_TRY(nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b, nullptr, nullptr,
                             w.emb, B * T, kEmb, kEmb, kEmb, false, s));
   return nws_launch_rows_to_bct(w.emb, emb, B, kEmb, T, kEmb, s);
@@ -423,7 +469,7 @@ extern "C" int nws_stage_noise(NwsHandle ctx, const float* H, const float* noise
   cudaStream_t s = (cudaStream_t)stream;
   NWS_TRY(nws_launch_bct_to_rows(H, w.bands, B, kBands, T, kBandsPad, s));
   NWS_TRY(nws_launch_noise_spectrum(ctx, noise, w.xspec, T, s));
-  return nws_launch_noise_filter(ctx, w.bands, w.xspec, out, B, T, s);
+  return nws_launch_noise_filter(ctx, w.bands, w.xspec, out, B, T, 0, T, s);
 }
 
 extern "C" int nws_stage_reverb(NwsHandle ctx, const float* x, float* out, int B, int N, void* workspace,

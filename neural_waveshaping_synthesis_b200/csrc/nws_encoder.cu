@@ -79,7 +79,7 @@ __device__ __forceinline__ float nws_sigmoid(float x) { return 1.0f / (1.0f + ex
 __global__ void __launch_bounds__(kGates, 1)
 nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, const float* __restrict__ b_ih,
                const float* __restrict__ b_hh, const float* __restrict__ control, int ctrl_channels,
-               float* __restrict__ hbuf, int T) {
+               float* __restrict__ hbuf, int T, int t_begin, int t_end, float* __restrict__ h_state) {
   const int b = blockIdx.x, r = threadIdx.x, lane = r & 31, row0 = r & ~31;
   __shared__ __align__(16) float h_s[2][kEmb];
   __shared__ float pre_rz[2 * kEmb];
@@ -92,13 +92,15 @@ nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, c
   const float wi0 = w_ih[r * 2], wi1 = w_ih[r * 2 + 1], bi = b_ih[r], bh = b_hh[r];
   const float* c0 = control + (size_t)b * ctrl_channels * T;
   const float* c1 = c0 + T;
-  if (r < kEmb) h_s[0][r] = 0.0f;
-  float x0 = c0[0], x1 = c1[0];
+  // steps [t_begin, t_end): the recurrence can be run in time blocks (h carried through h_state) so that the
+  // rest of the forward can start on the frames that are already encoded
+  if (r < kEmb) h_s[t_begin & 1][r] = t_begin > 0 ? h_state[(size_t)b * kEmb + r] : 0.0f;
+  float x0 = c0[t_begin], x1 = c1[t_begin];
   __syncthreads();
 
-  for (int t = 0; t < T; ++t) {
+  for (int t = t_begin; t < t_end; ++t) {
     const float* h = h_s[t & 1];
-    const float nx0 = t + 1 < T ? c0[t + 1] : 0.0f, nx1 = t + 1 < T ? c1[t + 1] : 0.0f;  // prefetch
+    const float nx0 = t + 1 < t_end ? c0[t + 1] : 0.0f, nx1 = t + 1 < t_end ? c1[t + 1] : 0.0f;  // prefetch
     const float4 hv = *reinterpret_cast<const float4*>(h + 4 * lane);
     float v[16];
 #pragma unroll
@@ -133,13 +135,14 @@ nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, c
     x0 = nx0; x1 = nx1;
     __syncthreads();
   }
+  if (h_state && r < kEmb) h_state[(size_t)b * kEmb + r] = h_s[t_end & 1][r];
 }
 
 int nws_launch_gru(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, int B, int T,
-                   cudaStream_t s) {
+                   int t_begin, int t_end, float* h_state, cudaStream_t s) {
   const float* p = ctx->packed;
   nws_gru_kernel<<<B, kGates, 0, s>>>(p + ctx->lay.gru_whh, p + ctx->lay.gru_wih, p + ctx->lay.gru_bih,
-                                      p + ctx->lay.gru_bhh, control, ctrl_channels, hbuf, T);
+                                      p + ctx->lay.gru_bhh, control, ctrl_channels, hbuf, T, t_begin, t_end, h_state);
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }

@@ -88,6 +88,7 @@ struct NwsReverbPlan {
 };
 
 constexpr int kMaxPlans = 8;
+constexpr int kMaxTimeBlocks = 64;   // pipelined forward: time blocks of 128 frames (longer utterances run serially)
 constexpr int kTwMaster = 4096;  // master twiddle table: W_4096^m, m < 2048
 
 struct NwsContext {
@@ -110,6 +111,11 @@ struct NwsContext {
   float shaper_inner_bound = 1e30f;   // max_j(|b_j| + sum_i |W_ji|) over shaper layers 2-4 (set by nws_load_weights)
   int audio_impl = 1;          // 1 = tcgen05 harmonic mixer (nws_audio_tc.cu), 0 = fp32 SIMT (nws_audio.cu)
   int device = 0;
+  // pipelined forward: the GRU runs in time blocks on an internal stream while the main stream renders the
+  // blocks already encoded
+  int pipeline = 1;
+  cudaStream_t enc_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_block[kMaxTimeBlocks] = {};
   // optional per-stage timing of nws_forward (cudaEvents on the launch stream)
   bool profile = false;
   cudaEvent_t ev[2 * 10] = {};
@@ -132,7 +138,8 @@ struct NwsWorkspace {
   float2* xspec;      // [T][kBandsPad]
   float* dry;         // [B][N]
   float* scratch;     // [M][256]  layout conversion for the stage entry points
-  int* counters;      // [16] tile counters of the dynamic schedulers
+  int* counters;      // [kMaxTimeBlocks] tile counters of the dynamic schedulers
+  float* h_state;     // [B][128] GRU state carried between time blocks
   float2* rev;        // [ceil(B/2)][L]
   size_t total;
 };
@@ -176,7 +183,8 @@ inline bool nws_first_use_on_device(bool* flags) {
 // ------------------------------------------------------------------ kernel launchers (one per .cu)
 // nws_encoder.cu
 int nws_launch_phase_carry(const float* f0, double* carry, int B, int T, cudaStream_t s);
-int nws_launch_gru(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, int B, int T, cudaStream_t s);
+int nws_launch_gru(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, int B, int T,
+                   int t_begin, int t_end, float* h_state, cudaStream_t s);
 int nws_launch_linear(const float* X, const float* Wt, const float* bias, const float* ln_g, const float* ln_b,
                       float* Y, int M, int n_out, int ldw, int ldy, bool ln_act, cudaStream_t s);
 int nws_launch_td_mlp(const NwsContext* ctx, int which, const float* emb, float* act0, float* act1, float* out,
@@ -193,7 +201,8 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
                         int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s);
 size_t nws_mlp_tc_blob_floats();
 int nws_launch_mlp_tc_pack(NwsContext* ctx, const float* const* tensors, cudaStream_t s);
-int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, cudaStream_t s);
+int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, int T, int t_begin,
+                      int t_end, cudaStream_t s);
 int nws_launch_pair_lut(NwsContext* ctx, cudaStream_t s);
 int nws_launch_build_lut(const NwsContext* ctx, const float* points, float* lut, int table_size, float tmin,
                          float tmax, cudaStream_t s);
@@ -201,7 +210,7 @@ int nws_launch_pack_weights(NwsContext* ctx, const float* const* tensors, cudaSt
 // nws_noise.cu
 int nws_launch_noise_spectrum(const NwsContext* ctx, const float* noise, float2* xspec, int T, cudaStream_t s);
 int nws_launch_noise_filter(const NwsContext* ctx, const float* bands, const float2* xspec, float* out, int B, int T,
-                            cudaStream_t s);
+                            int hop_begin, int hop_end, cudaStream_t s);
 // nws_reverb.cu
 int nws_reverb_get_plan(NwsContext* ctx, int fft_len, cudaStream_t s, NwsReverbPlan** out);
 int nws_launch_reverb(NwsContext* ctx, const float* x, float* out, float2* work, int B, int N, cudaStream_t s);

@@ -45,6 +45,8 @@ struct MlpTcParams {
   float* film;            // [M][256]
   float* bands;           // [M][132]
   int M;
+  int T, t_begin, t_end;  // frames [t_begin, t_end) of every utterance (T frames each); tiles never straddle utterances
+                          // when a sub-range is processed; t_begin = 0, t_end = T, T = M processes the flat [M] array
   int split;              // 1: even CTAs run blocks 0-5 (proj + FiLM chain), odd CTAs blocks 6-11 (proj + noise chain) of a tile
 };
 
@@ -100,7 +102,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
   __shared__ int fault_s;
   __shared__ __align__(16) float vec_s[kBlocks * kVecStride];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = (p.M + 127) / 128;
+  const int seg = p.t_end - p.t_begin, tiles_per_seg = (seg + 127) / 128;
+  const int n_tiles = (p.M / p.T) * tiles_per_seg;
   // work items: a tile, or (split) half of a tile's block sequence — the two halves are self-contained
   const int item0 = p.split ? blockIdx.x >> 1 : blockIdx.x, item_step = p.split ? gridDim.x >> 1 : gridDim.x;
   const int b_begin = p.split ? (blockIdx.x & 1) * 6 : 0, b_end = p.split ? b_begin + 6 : kBlocks;
@@ -193,8 +196,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
     uint32_t n_blk = 0;
     bool ok = true;
     for (int tile = item0; tile < n_tiles && ok; tile += item_step) {
-      const int row = tile * 128 + tid;
-      const bool valid = row < p.M;
+      const int ub = tile / tiles_per_seg, tk = tile - ub * tiles_per_seg;
+      const int row = ub * p.T + p.t_begin + tk * 128 + tid;
+      const bool valid = tk * 128 + tid < seg;
       const float* hrow = p.h + (size_t)(valid ? row : 0) * kEmb;
       for (int b = b_begin; b < b_end && ok; ++b, ++n_blk) {
         const MlpBlockDesc d = p.blk[b];
@@ -369,7 +373,8 @@ int nws_launch_mlp_tc_pack(NwsContext* ctx, const float* const* tensors, cudaStr
   return NWS_OK;
 }
 
-int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, cudaStream_t s) {
+int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, int T, int t_begin,
+                      int t_end, cudaStream_t s) {
   MlpTcParams p{};
   const NwsPackedLayout& L = ctx->lay;
   // block -> (distinct weight block, N, kind, col0, new_a, bias, gamma, beta)
@@ -393,13 +398,15 @@ int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, flo
   p.blk[4].bias = L.mlp[0].b_out; p.blk[5].bias = L.mlp[0].b_out + 128;
   p.blk[10].bias = L.mlp[1].b_out; p.blk[11].bias = L.mlp[1].b_out + 128;
   p.packed = ctx->packed; p.w_tc = ctx->mlp_tc; p.h = hbuf; p.film = film; p.bands = bands; p.M = M;
+  if (t_begin == 0 && t_end == T) { p.T = M; p.t_begin = 0; p.t_end = M; }   // whole batch: one flat array of M frames
+  else { p.T = T; p.t_begin = t_begin; p.t_end = t_end; }
 
   static bool attr_done[64] = {};
   const int smem = kSlots * kSlotBytes;
   if (nws_first_use_on_device(attr_done)) {
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
-  const int tiles = (M + 127) / 128;
+  const int tiles = (M / p.T) * ((p.t_end - p.t_begin + 127) / 128);
   p.split = 2 * tiles <= ctx->sm_count ? 1 : 0;   // few tiles: halve the dependent-block chain per CTA (latency)
   const int grid = p.split ? 2 * tiles : (tiles < ctx->sm_count ? tiles : ctx->sm_count);
   nws_mlp_tc_kernel<<<grid, kMlpThreads, smem, s>>>(p, nullptr);

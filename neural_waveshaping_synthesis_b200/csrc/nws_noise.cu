@@ -63,12 +63,14 @@ constexpr int kNoiseFrames = kNoiseHops + 1;
 __global__ void __launch_bounds__(256) nws_noise_filter_kernel(const float* __restrict__ bands,
                                                                const float2* __restrict__ xspec,
                                                                const float2* __restrict__ tw_master,
-                                                               float* __restrict__ out, int T) {
+                                                               float* __restrict__ out, int T, int hop_begin,
+                                                               int hop_end) {
   __shared__ float2 buf_a[2][256], buf_b[2][256], tw_s[128];
   __shared__ float hs[2][2][kBandsPad];           // [fft][frame of pair][band]
   __shared__ float y_s[kNoiseFrames][256];
-  const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kNoiseHops;
+  const int tid = threadIdx.x, b = blockIdx.y, t0 = hop_begin + blockIdx.x * kNoiseHops;   // hops [hop_begin, hop_end)
   const int g = tid >> 7, j = tid & 127;          // g: which of the two concurrent FFTs
+  const int f_lim = hop_end < T ? hop_end : T;    // frames >= hop_end are not needed (and may not be encoded yet)
   nws_load_tw256(tw_s, tw_master, tid, 256);
 
   for (int pair0 = 0; pair0 < kNoiseFrames / 2; pair0 += 2) {
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) nws_noise_filter_kernel(const float* __re
     for (int q = 0; q < 2; ++q) {
       const int f = q == 0 ? fa : fb;
       for (int k = j; k < kBandsPad; k += 128)
-        hs[g][q][k] = (f >= 0 && f < T && k < kBands) ? bands[((size_t)b * T + f) * kBandsPad + k] : 0.f;
+        hs[g][q][k] = (f >= 0 && f < f_lim && k < kBands) ? bands[((size_t)b * T + f) * kBandsPad + k] : 0.f;
     }
     __syncthreads();
     // Z[k] = Ya[k] + i Yb[k], Y = X * Hw, Hermitian-extended to 256 bins
@@ -87,12 +89,12 @@ __global__ void __launch_bounds__(256) nws_noise_filter_kernel(const float* __re
       const int km = kk == 0 ? 1 : kk - 1, kp = kk == 128 ? 127 : kk + 1;
       const float sgn = (kk & 1) ? -1.f : 1.f;
       float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
-      if (fa >= 0 && fa < T) {
+      if (fa >= 0 && fa < f_lim) {
         const float hw = sgn * fmaf(0.25f, hs[g][0][km] + hs[g][0][kp], 0.5f * hs[g][0][kk]);
         const float2 x = xspec[(size_t)fa * kBandsPad + kk];
         ya = make_float2(x.x * hw, x.y * hw);
       }
-      if (fb >= 0 && fb < T) {
+      if (fb >= 0 && fb < f_lim) {
         const float hw = sgn * fmaf(0.25f, hs[g][1][km] + hs[g][1][kp], 0.5f * hs[g][1][kk]);
         const float2 x = xspec[(size_t)fb * kBandsPad + kk];
         yb = make_float2(x.x * hw, x.y * hw);
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(256) nws_noise_filter_kernel(const float* __re
   const int N = T * kHop;
   for (int i = tid; i < kNoiseHops * kHop; i += 256) {
     const int h = i >> 7, r = i & 127, t = t0 + h;
-    if (t >= T) break;
+    if (t >= hop_end) break;
     const float cur = y_s[h + 1][r];
     const float v = t == 0 ? cur : 0.5f * (y_s[h][kHop + r] + cur);
     out[(size_t)b * N + t * kHop + r] = v;
@@ -124,9 +126,9 @@ __global__ void __launch_bounds__(256) nws_noise_filter_kernel(const float* __re
 }
 
 int nws_launch_noise_filter(const NwsContext* ctx, const float* bands, const float2* xspec, float* out, int B, int T,
-                            cudaStream_t s) {
-  dim3 grid((T + kNoiseHops - 1) / kNoiseHops, B);
-  nws_noise_filter_kernel<<<grid, 256, 0, s>>>(bands, xspec, ctx->tw_master, out, T);
+                            int hop_begin, int hop_end, cudaStream_t s) {
+  dim3 grid((hop_end - hop_begin + kNoiseHops - 1) / kNoiseHops, B);
+  nws_noise_filter_kernel<<<grid, 256, 0, s>>>(bands, xspec, ctx->tw_master, out, T, hop_begin, hop_end);
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }

@@ -172,6 +172,10 @@ class NwsEngine:
         """1 = tcgen05 harmonic mixer (default), 0 = fp32 SIMT mixer."""
         _lib.check(self.lib.nws_set_audio_impl(self.handle, impl))
 
+    def set_pipeline(self, enable: bool):
+        """Pipelined forward (GRU time blocks on an internal stream overlapped with rendering); default on."""
+        _lib.check(self.lib.nws_set_pipeline(self.handle, 1 if enable else 0))
+
     def set_mlp_impl(self, impl: int):
         """1 = tcgen05 MLP chain (default), 0 = fp32 SIMT layer kernels."""
         _lib.check(self.lib.nws_set_mlp_impl(self.handle, impl))
