@@ -58,9 +58,16 @@ extern "C" int nws_create(const NwsConfig* cfg, NwsHandle* out) {
   int rc = nws_make_twiddle_master(ctx);
   if (rc) { cudaFree(ctx->packed); delete ctx; return rc; }
   // internal encoder stream + fork/join events of the pipelined forward (timing disabled: cheaper)
-  e = cudaStreamCreateWithFlags(&ctx->enc_stream, cudaStreamNonBlocking);
+  {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    e = cudaStreamCreateWithPriority(&ctx->enc_stream, cudaStreamNonBlocking, prio_hi);   // GRU CTAs first when SMs free up
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   for (int i = 0; i < kMaxTimeBlocks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_block[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_early_ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_early_done, cudaEventDisableTiming);
   if (e != cudaSuccess) { nws_set_error("nws_create: %s", cudaGetErrorString(e)); nws_destroy(ctx); return NWS_ERR_CUDA; }
   *out = ctx;
   return NWS_OK;
@@ -72,6 +79,9 @@ extern "C" int nws_destroy(NwsHandle ctx) {
   for (int i = 0; i < 2 * kStCount; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->enc_stream) { cudaStreamSynchronize(ctx->enc_stream); cudaStreamDestroy(ctx->enc_stream); }
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->ev_early_ready) cudaEventDestroy(ctx->ev_early_ready);
+  if (ctx->ev_early_done) cudaEventDestroy(ctx->ev_early_done);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   for (int i = 0; i < kMaxTimeBlocks; ++i)
     if (ctx->ev_block[i]) cudaEventDestroy(ctx->ev_block[i]);
@@ -335,7 +345,7 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
 
   const int n_blocks = (T + 127) / 128;
   const bool pipelined = ctx->pipeline && ctx->mlp_impl && ctx->audio_impl && !ctx->profile && ctx->enc_stream &&
-                         n_blocks >= 2 && n_blocks <= kMaxTimeBlocks && (long long)B * T >= 4096;
+                         ctx->aux_stream && n_blocks >= 2 && n_blocks <= kMaxTimeBlocks && (long long)B * T >= 4096 && B + 16 <= ctx->sm_count;
   if (pipelined) {
     // The GRU is 500 dependent steps on B SMs; everything downstream only needs the frames already encoded.
     // So the recurrence runs in 128-frame time blocks on an internal stream, and the main stream renders
@@ -349,17 +359,27 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
       NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, t0, t1, w.h_state, g));
       NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[j], g));
     }
+    // Main stream: MLP chain + noise hops of block j as soon as it is encoded (short kernels that interleave
+    // with the GRU blocks).  Audio: the hops of block 0 start early on the auxiliary stream, on the SMs the
+    // GRU leaves free (persistent CTAs, capped so they never squat on the encoder's SMs); the rest of the
+    // hops run with a full grid once everything is encoded and overlap the tail of the early launch.
+    const int early_end = 127;   // hops [0, 127) only need FiLM frames 0..127 = block 0
     for (int j = 0; j < n_blocks; ++j) {
       const int t0 = j * 128, t1 = t0 + 128 < T ? t0 + 128 : T;
       NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[j], 0));
       NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, t0, t1, s));
       NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, t0, t1, s));
-      // hop t interpolates FiLM frames t-1..t+1: the block's audio lags one hop, the last block catches up
-      const int a0 = t0 > 0 ? t0 - 1 : 0, a1 = j + 1 < n_blocks ? t1 - 1 : T;
-      if (a1 > a0)
-        NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, a0, a1,
-                                    w.counters + j, use_lut, s));
+      if (j == 0) {
+        NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_ready, s));
+        NWS_CUDA_OK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_early_ready, 0));
+        NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, early_end,
+                                    w.counters, use_lut, ctx->aux_stream, ctx->sm_count - B));
+        NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_done, ctx->aux_stream));
+      }
     }
+    NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, early_end, T,
+                                w.counters + 1, use_lut, s));
+    NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_early_done, 0));
   } else {
     NWS_STAGE(ctx, kStGru, s, nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, T, nullptr, s));
     if (ctx->mlp_impl) {

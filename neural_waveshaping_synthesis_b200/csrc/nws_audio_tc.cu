@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
 
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
-                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s) {
+                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s, int max_ctas) {
   NwsAudioParams p{};
   const float* w = ctx->packed;
   p.f0 = f0; p.carry = carry; p.film = film; p.u_phase = u_phase;
@@ -395,7 +395,8 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   }
   const long long tiles = (long long)B * (t_end - t_begin);
   const long long want = (tiles + kWgs - 1) / kWgs;
-  const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
+  const int cap = max_ctas > 0 && max_ctas < ctx->sm_count ? max_ctas : ctx->sm_count;   // SMs left to a concurrent encoder
+  const int grid = (int)(want < cap ? want : cap);
   const float* wu = w + ctx->lay.hmix_umma;
   const bool direct = ctx->shaper_inner_bound <= 8.0f;   // see NWS_SHAPER_SIN_INNER
   if (use_lut && !exciter_out) nws_audio_tc_kernel<true, false, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);

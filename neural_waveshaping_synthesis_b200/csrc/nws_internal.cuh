@@ -114,7 +114,8 @@ struct NwsContext {
   // pipelined forward: the GRU runs in time blocks on an internal stream while the main stream renders the
   // blocks already encoded
   int pipeline = 1;
-  cudaStream_t enc_stream = nullptr;
+  cudaStream_t enc_stream = nullptr, aux_stream = nullptr;
+  cudaEvent_t ev_early_ready = nullptr, ev_early_done = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_block[kMaxTimeBlocks] = {};
   // optional per-stage timing of nws_forward (cudaEvents on the launch stream)
   bool profile = false;
@@ -198,7 +199,7 @@ int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry
                      int use_lut, cudaStream_t s);
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
-                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s);
+                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s, int max_ctas = 0);
 size_t nws_mlp_tc_blob_floats();
 int nws_launch_mlp_tc_pack(NwsContext* ctx, const float* const* tensors, cudaStream_t s);
 int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, int T, int t_begin,

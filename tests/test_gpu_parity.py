@@ -414,7 +414,8 @@ def test_cuda_graph_capture_and_replay():
 
 def test_pipelined_forward_equals_serial():
     """The pipelined forward (GRU time blocks on an internal stream, rendering overlapped) runs the same
-    arithmetic as the serial one: bit-identical output, including a ragged last block and B not a multiple of 2."""
+    arithmetic as the serial one — equal to fp32 round-off (the noise branch pairs frames differently in its
+    two-for-one FFTs when hops are rendered block by block), deterministic, including a ragged last block."""
     for tag, fast, B, T in (("vn", True, 64, 500), ("randinit", False, 9, 461)):
         m, w = _model(tag, fast)
         gen = torch.Generator().manual_seed(B)
@@ -431,4 +432,5 @@ def test_pipelined_forward_equals_serial():
             piped2 = m(f0, control, **args)
         torch.cuda.synchronize()
         assert torch.isfinite(serial).all()
-        assert torch.equal(serial, piped) and torch.equal(piped, piped2), (tag, err(serial, piped))
+        assert torch.equal(piped, piped2)
+        assert err(serial, piped)[0] < 1e-6 * max(1.0, float(serial.abs().max())), (tag, err(serial, piped))
