@@ -323,6 +323,32 @@ extern "C" int nws_get_stage_times(NwsHandle ctx, float* ms_out, int n) {
   return NWS_OK;
 }
 
+// Development aid: NWS_TIMELINE=1 prints when each kernel of the pipelined forward finished, relative to
+// the fork point (timed events on the three streams; synchronises — never enabled in measurements).
+struct NwsTimeline {
+  bool on = false;
+  int n = 0;
+  cudaEvent_t ev[128];
+  const char* name[128];
+  void mark(const char* nm, cudaStream_t st) {
+    if (!on || n >= 128) return;
+    if (!ev[n]) cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], st);
+    name[n++] = nm;
+  }
+  void dump() {
+    if (!on || n < 2) return;
+    cudaDeviceSynchronize();
+    for (int i = 1; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[0], ev[i]);
+      fprintf(stderr, "[nws timeline] %-18s done at %8.3f ms\n", name[i], ms);
+    }
+    n = 0;
+  }
+};
+static NwsTimeline g_tl;
+
 extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control, int ctrl_channels,
                            const float* u_phase, const float* noise, uint64_t seed, uint64_t offset, float* out,
                            int B, int T, int use_lut, void* workspace, size_t workspace_bytes, void* stream) {
@@ -352,12 +378,15 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
     // block j (MLP chain -> noise hops -> audio hops) as soon as block j is encoded, on the SMs the GRU does
     // not occupy (the audio kernel claims its tiles dynamically).  Stream/event dependencies only.
     cudaStream_t g = ctx->enc_stream;
+    g_tl.on = getenv("NWS_TIMELINE") != nullptr;
+    g_tl.mark("fork", s);
     NWS_CUDA_OK(cudaEventRecord(ctx->ev_fork, s));
     NWS_CUDA_OK(cudaStreamWaitEvent(g, ctx->ev_fork, 0));
     for (int j = 0; j < n_blocks; ++j) {
       const int t0 = j * 128, t1 = t0 + 128 < T ? t0 + 128 : T;
       NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, t0, t1, w.h_state, g));
       NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[j], g));
+      g_tl.mark("gru block", g);
     }
     // Main stream: MLP chain + noise hops of block j as soon as it is encoded (short kernels that interleave
     // with the GRU blocks).  Audio: the hops of block 0 start early on the auxiliary stream, on the SMs the
@@ -368,17 +397,21 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
       const int t0 = j * 128, t1 = t0 + 128 < T ? t0 + 128 : T;
       NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[j], 0));
       NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, t0, t1, s));
+      g_tl.mark("mlp block", s);
       NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, t0, t1, s));
+      g_tl.mark("noise block", s);
       if (j == 0) {
         NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_ready, s));
         NWS_CUDA_OK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_early_ready, 0));
         NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, early_end,
                                     w.counters, use_lut, ctx->aux_stream, ctx->sm_count - B));
         NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_done, ctx->aux_stream));
+        g_tl.mark("audio early", ctx->aux_stream);
       }
     }
     NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, early_end, T,
                                 w.counters + 1, use_lut, s));
+    g_tl.mark("audio rest", s);
     NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_early_done, 0));
   } else {
     NWS_STAGE(ctx, kStGru, s, nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, T, nullptr, s));
@@ -398,6 +431,7 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   }
   // reverb
   NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb(ctx, w.dry, out, w.rev, B, N, s));
+  if (g_tl.on) { g_tl.mark("reverb", s); g_tl.dump(); }
   return NWS_OK;
 }
 
