@@ -371,44 +371,42 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
 
   const int n_blocks = (T + 127) / 128;
   const bool pipelined = ctx->pipeline && ctx->mlp_impl && ctx->audio_impl && !ctx->profile && ctx->enc_stream &&
-                         ctx->aux_stream && n_blocks >= 2 && n_blocks <= kMaxTimeBlocks && (long long)B * T >= 4096 && B + 16 <= ctx->sm_count;
+                         ctx->aux_stream && n_blocks >= 3 && (long long)B * T >= 4096 && B + 16 <= ctx->sm_count;
   if (pipelined) {
-    // The GRU is 500 dependent steps on B SMs; everything downstream only needs the frames already encoded.
-    // So the recurrence runs in 128-frame time blocks on an internal stream, and the main stream renders
-    // block j (MLP chain -> noise hops -> audio hops) as soon as block j is encoded, on the SMs the GRU does
-    // not occupy (the audio kernel claims its tiles dynamically).  Stream/event dependencies only.
-    cudaStream_t g = ctx->enc_stream;
+    // The GRU is T dependent steps on B SMs; everything downstream only needs the frames already encoded.
+    // The recurrence is cut after 128 frames: while the encoder stream runs the remaining steps, the head
+    // block goes through the MLP chain and the noise branch and its audio hops are rendered on the SMs the
+    // GRU does not occupy (persistent CTAs, capped; tiles claimed dynamically).  Stream/event dependencies only.
+    cudaStream_t g = ctx->enc_stream, aux = ctx->aux_stream;
     g_tl.on = getenv("NWS_TIMELINE") != nullptr;
     g_tl.mark("fork", s);
     NWS_CUDA_OK(cudaEventRecord(ctx->ev_fork, s));
     NWS_CUDA_OK(cudaStreamWaitEvent(g, ctx->ev_fork, 0));
-    for (int j = 0; j < n_blocks; ++j) {
-      const int t0 = j * 128, t1 = t0 + 128 < T ? t0 + 128 : T;
-      NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, t0, t1, w.h_state, g));
-      NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[j], g));
-      g_tl.mark("gru block", g);
-    }
-    // Main stream: MLP chain + noise hops of block j as soon as it is encoded (short kernels that interleave
-    // with the GRU blocks).  Audio: the hops of block 0 start early on the auxiliary stream, on the SMs the
-    // GRU leaves free (persistent CTAs, capped so they never squat on the encoder's SMs); the rest of the
-    // hops run with a full grid once everything is encoded and overlap the tail of the early launch.
-    const int early_end = 127;   // hops [0, 127) only need FiLM frames 0..127 = block 0
-    for (int j = 0; j < n_blocks; ++j) {
-      const int t0 = j * 128, t1 = t0 + 128 < T ? t0 + 128 : T;
-      NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[j], 0));
-      NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, t0, t1, s));
-      g_tl.mark("mlp block", s);
-      NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, t0, t1, s));
-      g_tl.mark("noise block", s);
-      if (j == 0) {
-        NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_ready, s));
-        NWS_CUDA_OK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_early_ready, 0));
-        NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, early_end,
-                                    w.counters, use_lut, ctx->aux_stream, ctx->sm_count - B));
-        NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_done, ctx->aux_stream));
-        g_tl.mark("audio early", ctx->aux_stream);
-      }
-    }
+    // encoder stream: frames [0,128), then the rest (hidden state carried in h_state)
+    const int t_split = 128, early_end = t_split - 1;   // hops [0,127) only need FiLM frames 0..127
+    NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, t_split, w.h_state, g));
+    NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[0], g));
+    g_tl.mark("gru head", g);
+    NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, t_split, T, w.h_state, g));
+    NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[1], g));
+    g_tl.mark("gru rest", g);
+    // caller's stream: head block -> early audio on the auxiliary stream, on the SMs the GRU leaves free
+    NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[0], 0));
+    NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, 0, t_split, s));
+    NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, 0, t_split, s));
+    g_tl.mark("mlp+noise head", s);
+    NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_ready, s));
+    NWS_CUDA_OK(cudaStreamWaitEvent(aux, ctx->ev_early_ready, 0));
+    NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, early_end, w.counters,
+                                use_lut, aux, ctx->sm_count - B));
+    NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_done, aux));
+    g_tl.mark("audio head", aux);
+    // the rest, once everything is encoded; its audio overlaps the tail of the early launch
+    NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[1], 0));
+    NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, t_split, T, s));
+    g_tl.mark("mlp rest", s);
+    NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, t_split, T, s));
+    g_tl.mark("noise rest", s);
     NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, early_end, T,
                                 w.counters + 1, use_lut, s));
     g_tl.mark("audio rest", s);
