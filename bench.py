@@ -291,39 +291,28 @@ def run_b200(args):
                 stage_acc[k] = stage_acc.get(k, 0.0) + v / args.steps
         eng.set_profiling(False)
 
-        # ---- end to end through the public module API: every step copies its inputs from pinned host memory,
-        # runs the forward and reads the audio back to pinned host memory.  As in scripts/resynthesise_dataset.py
-        # the D2H of step i runs on a copy stream (double-buffered) while step i+1 computes; every byte of every
-        # step is inside the timed region, which ends when the last result has landed on the host.
-        out_host = [torch.empty(B, N, dtype=torch.float32).pin_memory() for _ in range(2)]
-        copy_stream = torch.cuda.Stream(dev)
-        copied = [None, None]
+        # ---- end to end through the public API for host-resident batches (streaming.HostPipeline, the loop of
+        # scripts/resynthesise_dataset.py): every step copies its inputs from pinned host memory, runs the forward
+        # and reads the audio back to pinned host memory; upload of step i+1 and download of step i-1 overlap the
+        # forward of step i.  Every byte of every step is inside the timed region, which ends when the last
+        # result has landed on the host.
+        from neural_waveshaping_synthesis_b200.streaming import HostPipeline
 
-        def e2e_step(i):
-            y = model(f0_host.to(dev, non_blocking=True), control_host.to(dev, non_blocking=True))
-            done = torch.cuda.Event()
-            done.record()
-            slot = i & 1
-            if copied[slot] is not None:
-                copied[slot].synchronize()          # the host buffer of step i-2 has been consumed
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done)
-                out_host[slot].copy_(y, non_blocking=True)
-                y.record_stream(copy_stream)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            copied[slot] = ev
+        def e2e_run(n):
+            pipe = HostPipeline(model, dev)
+            landed = 0
+            for _, audio in pipe.run((f0_host, control_host) for _ in range(n)):
+                landed += 1
+            assert landed == n and audio.shape == (B, N)
+            return pipe
 
-        for i in range(args.warmup):
-            e2e_step(i)
+        e2e_run(args.warmup)
         barrier()
-        copy_stream.synchronize()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            e2e_step(i)
+        pipe = e2e_run(args.steps)
         torch.cuda.synchronize(dev)
-        copy_stream.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.steps
+        h2d_per_step, d2h_per_step = pipe.h2d_bytes // args.steps, pipe.d2h_bytes // args.steps
 
     # ---- aggregate over ranks: time = max over ranks, samples = sum
     from neural_waveshaping_synthesis_b200.sharding import aggregate_throughput
@@ -351,7 +340,7 @@ def run_b200(args):
         "rtf_batch": (step_ms_max * 1e-3) / args.seconds,
         "config": workload_config(args),
         "e2e": {"value": total_samples / (e2e_ms_max * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms_max,
-                "h2d_bytes_per_step": B * 3 * T * 4, "d2h_bytes_per_step": B * N * 4},
+                "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "nws_audio_tc_kernel<%s>" % ("LUT" if args.variant == "fastnewt" else "MLP"),

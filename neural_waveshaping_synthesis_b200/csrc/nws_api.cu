@@ -360,6 +360,30 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   cudaStream_t s = (cudaStream_t)stream;
   const int M = B * T, N = T * kHop;
 
+  const int n_blocks = (T + 127) / 128;
+  const bool pipelined = ctx->pipeline && ctx->mlp_impl && ctx->audio_impl && !ctx->profile && ctx->enc_stream &&
+                         ctx->aux_stream && n_blocks >= 3 && (long long)B * T >= 4096 && B + 16 <= ctx->sm_count;
+  const int t_split = 128, early_end = t_split - 1;   // pipelined: hops [0,127) only need FiLM frames 0..127
+  if (pipelined) {
+    // The GRU is T dependent steps on B SMs; everything downstream only needs the frames already encoded.
+    // The recurrence is cut after 128 frames: while the encoder stream runs the remaining steps, the head
+    // block goes through the MLP chain and the noise branch and its audio hops are rendered on the SMs the
+    // GRU does not occupy (persistent CTAs, capped; tiles claimed dynamically).  Stream/event dependencies only.
+    // The encoder only reads `control`, so it is forked first: the draws, phase carries and noise spectrum
+    // below run beside its first steps instead of ahead of them.
+    cudaStream_t g = ctx->enc_stream;
+    g_tl.on = getenv("NWS_TIMELINE") != nullptr;
+    g_tl.mark("fork", s);
+    NWS_CUDA_OK(cudaEventRecord(ctx->ev_fork, s));
+    NWS_CUDA_OK(cudaStreamWaitEvent(g, ctx->ev_fork, 0));
+    NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, t_split, w.h_state, g));
+    NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[0], g));
+    g_tl.mark("gru head", g);
+    NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, t_split, T, w.h_state, g));
+    NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[1], g));
+    g_tl.mark("gru rest", g);
+  }
+
   if (!u_phase || !noise) {  // the forward's own draws (generators.py:55, :30); injected ones are kept
     NWS_STAGE(ctx, kStRng, s, nws_launch_rng(u_phase ? nullptr : w.u_phase, noise ? nullptr : w.noise, N - 1, seed, offset, s));
     if (!u_phase) u_phase = w.u_phase;
@@ -368,28 +392,10 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   // hop rate: phase carries, control encoder, FiLM parameters, noise band gains
   NWS_STAGE(ctx, kStCarry, s, nws_launch_phase_carry(f0, w.carry, B, T, s));
   NWS_STAGE(ctx, kStNoiseSpec, s, nws_launch_noise_spectrum(ctx, noise, w.xspec, T, s));
+  g_tl.mark("draws+carry+spec", s);
 
-  const int n_blocks = (T + 127) / 128;
-  const bool pipelined = ctx->pipeline && ctx->mlp_impl && ctx->audio_impl && !ctx->profile && ctx->enc_stream &&
-                         ctx->aux_stream && n_blocks >= 3 && (long long)B * T >= 4096 && B + 16 <= ctx->sm_count;
   if (pipelined) {
-    // The GRU is T dependent steps on B SMs; everything downstream only needs the frames already encoded.
-    // The recurrence is cut after 128 frames: while the encoder stream runs the remaining steps, the head
-    // block goes through the MLP chain and the noise branch and its audio hops are rendered on the SMs the
-    // GRU does not occupy (persistent CTAs, capped; tiles claimed dynamically).  Stream/event dependencies only.
-    cudaStream_t g = ctx->enc_stream, aux = ctx->aux_stream;
-    g_tl.on = getenv("NWS_TIMELINE") != nullptr;
-    g_tl.mark("fork", s);
-    NWS_CUDA_OK(cudaEventRecord(ctx->ev_fork, s));
-    NWS_CUDA_OK(cudaStreamWaitEvent(g, ctx->ev_fork, 0));
-    // encoder stream: frames [0,128), then the rest (hidden state carried in h_state)
-    const int t_split = 128, early_end = t_split - 1;   // hops [0,127) only need FiLM frames 0..127
-    NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, t_split, w.h_state, g));
-    NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[0], g));
-    g_tl.mark("gru head", g);
-    NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, t_split, T, w.h_state, g));
-    NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[1], g));
-    g_tl.mark("gru rest", g);
+    cudaStream_t aux = ctx->aux_stream;
     // caller's stream: head block -> early audio on the auxiliary stream, on the SMs the GRU leaves free
     NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[0], 0));
     NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, 0, t_split, s));

@@ -37,31 +37,15 @@ def main(model_gin, model_checkpoint, dataset_root, dataset_split, output_path, 
     loader = torch.utils.data.DataLoader(data, batch_size=batch_size, num_workers=num_workers, pin_memory=True)
     model = build_model(model_gin, use_fastnewt, torch.device(device), checkpoint=model_checkpoint)
     sample_rate = int(model.sample_rate)
-    pending = None
-    copy_stream = torch.cuda.Stream(device)
-    with torch.no_grad():
+    from neural_waveshaping_synthesis_b200.streaming import HostPipeline
+
+    def batches():
         for batch in tqdm(loader):
-            f0 = batch["f0"].float().to(device, non_blocking=True)
-            control = batch["control"].float().to(device, non_blocking=True)
-            y = model(f0, control)
-            done = torch.cuda.Event()
-            done.record()
-            if pending is not None:            # finish the previous batch while this one computes
-                ev, names, target, host = pending
-                ev.synchronize()
-                _write(output_path, sample_rate, names, target, host.numpy())
-            host = torch.empty(y.shape, dtype=torch.float32).pin_memory()
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done)
-                host.copy_(y, non_blocking=True)
-                y.record_stream(copy_stream)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            pending = (ev, batch["name"], batch["audio"].float().numpy(), host)
-    if pending is not None:
-        ev, names, target, host = pending
-        ev.synchronize()
-        _write(output_path, sample_rate, names, target, host.numpy())
+            yield batch["f0"].float(), batch["control"].float(), (batch["name"], batch["audio"].float().numpy())
+
+    # upload of the next batch and download of the previous result overlap the forward of the current one
+    for (names, target), audio in HostPipeline(model, torch.device(device)).run(batches()):
+        _write(output_path, sample_rate, names, target, audio.numpy())
 
 
 if __name__ == "__main__":

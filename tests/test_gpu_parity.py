@@ -434,3 +434,27 @@ def test_pipelined_forward_equals_serial():
         assert torch.isfinite(serial).all()
         assert torch.equal(piped, piped2)
         assert err(serial, piped)[0] < 1e-6 * max(1.0, float(serial.abs().max())), (tag, err(serial, piped))
+
+
+def test_host_pipeline_matches_direct_forwards():
+    """streaming.HostPipeline (upload i+1 / forward i / download i-1 on three streams) returns, batch by batch,
+    exactly what direct forwards on the same inputs and the same RNG stream return — including a ragged last
+    batch and metadata passed through."""
+    from neural_waveshaping_synthesis_b200.streaming import HostPipeline
+    m, _ = _model("vn", True)
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(16, 64), (16, 64), (16, 64), (16, 64), (5, 37)]
+    batches = [((100.0 + 400.0 * torch.rand(B, 1, T, generator=gen)).pin_memory(),
+                torch.randn(B, 2, T, generator=gen).pin_memory(), "batch%d" % i) for i, (B, T) in enumerate(shapes)]
+    torch.manual_seed(11)
+    with torch.no_grad():
+        direct = [m(f0.cuda(), c.cuda()).cpu() for f0, c, _ in batches]
+    torch.manual_seed(11)
+    pipe = HostPipeline(m, "cuda:0")
+    got = [(meta, audio.clone()) for meta, audio in pipe.run(iter(batches))]
+    assert [g[0] for g in got] == [b[2] for b in batches]
+    for (meta, audio), ref in zip(got, direct):
+        assert audio.shape == ref.shape and torch.equal(audio, ref), meta
+    assert pipe.d2h_bytes == sum(B * T * 128 * 4 for B, T in shapes)
+    assert pipe.h2d_bytes == sum(B * T * 3 * 4 for B, T in shapes)
+    assert list(HostPipeline(m, "cuda:0").run(iter([]))) == []
