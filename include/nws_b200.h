@@ -204,8 +204,8 @@ int nws_set_audio_impl(NwsHandle handle, int impl);
 int nws_selftest_umma(const float* A, const float* B, float* D, int K, int swap_lbo_sbo, int* status, void* stream);
 
 /* Accuracy probe of the device sine implementations (csrc/nws_math.h): accurate polynomial version and
- * the SFU-based fast versions (3- and 2-term reduction) on x[0..n). */
-int nws_selftest_sin(const float* x, float* y_accurate, float* y_fast3, float* y_fast2, long long n, void* stream);
+ * the SFU-based versions (quarter-turn reduction + sin/cos select; full-turn reduction, one MUFU) on x[0..n). */
+int nws_selftest_sin(const float* x, float* y_accurate, float* y_quarter, float* y_turn, long long n, void* stream);
 
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */

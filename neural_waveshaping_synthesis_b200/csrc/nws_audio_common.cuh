@@ -3,16 +3,16 @@
 #pragma once
 #include "nws_internal.cuh"
 
-// Sine used inside the shaper MLP (1,600 evaluations per sample on the NEWT path): SFU-based, 2-term
-// reduction (arguments are a few tens of radians at most).  The LUT builder uses the accurate version so
+// Sine used inside the shaper MLP (1,600 evaluations per sample on the NEWT path): SFU-based with a
+// full-turn reduction (nws_sinf_turn).  The LUT builder uses the accurate version so
 // FastNEWT tables match the reference's to 1 ulp-level (see nws_build_lut_kernel).
-// MODE 0: polynomial sine everywhere (LUT builder).  MODE 1: SFU sine with 2-term reduction everywhere.
+// MODE 0: polynomial sine everywhere (LUT builder).  MODE 1: SFU sine with range reduction everywhere.
 // MODE 2: as 1 for the first layer (its argument scales with the input), and bare sin.approx for layers 2-4,
 // whose arguments are bounded by max_j(|b_j| + sum_i |W_ji|) because the previous layer's outputs are sines —
 // the bound is checked when the weights are loaded (nws_load_weights) and MODE 2 is used only if it is <= 8
 // (3.8 at most in the shipped checkpoints), where x/2pi keeps the error at the SFU's own 4e-7 level.
-#define NWS_SHAPER_SIN(x) (MODE == 0 ? nws_sinf(x) : nws_sinf_fast<2>(x))
-#define NWS_SHAPER_SIN_INNER(x) (MODE == 0 ? nws_sinf(x) : (MODE == 1 ? nws_sinf_fast<2>(x) : __sinf(x)))
+#define NWS_SHAPER_SIN(x) (MODE == 0 ? nws_sinf(x) : nws_sinf_turn(x))
+#define NWS_SHAPER_SIN_INNER(x) (MODE == 0 ? nws_sinf(x) : (MODE == 1 ? nws_sinf_turn(x) : __sinf(x)))
 
 struct NwsAudioParams {
   const float* f0;        // [B][T]

@@ -25,7 +25,7 @@
 #define NWS_OSC_FAST 1
 #endif
 #if NWS_OSC_FAST
-#define NWS_OSC_SIN(x) nws_sinf_fast<3>(x)
+#define NWS_OSC_SIN(x) nws_sinf_turn(x)
 #else
 #define NWS_OSC_SIN(x) nws_sinf(x)
 #endif
@@ -54,6 +54,10 @@ struct TcCfg {
 };
 
 __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+// Stage-operand-written barrier of (warpgroup, stage buffer): named barriers 5..12, 128 producer threads arrive
+// (non-blocking; their shared-memory stores are ordered before the consumer's wake-up), the MMA warp syncs.
+__device__ __forceinline__ void fill_arrive(int wg, int buf) { asm volatile("bar.arrive %0, 160;" ::"r"(5 + 2 * wg + buf) : "memory"); }
+__device__ __forceinline__ void fill_wait(int wg, int buf) { asm volatile("bar.sync %0, 160;" ::"r"(5 + 2 * wg + buf) : "memory"); }
 
 template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
@@ -89,7 +93,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
                                                                      int* __restrict__ fault) {
   using C = TcCfg<USE_LUT>;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t fill_bar[kWgs][2];   // stage operand written (4 arrivals: one per compute warp)
   __shared__ uint64_t free_bar[kWgs][2];   // the MMAs that read the stage have completed (tcgen05.commit)
   __shared__ double warp_tot[kWgs + 1][4];
   __shared__ uint32_t tmem_base_s;
@@ -118,7 +121,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   if (tid < 32) nws_tmem_alloc(&tmem_base_s, 64 * kWgs);
   if (tid == 0) {
     for (int i = 0; i < kWgs * 2; ++i) {
-      nws_mbar_init(&fill_bar[0][0] + i, 4);
       nws_mbar_init(&free_bar[0][0] + i, 1);
     }
     nws_fence_mbar_init();
@@ -140,27 +142,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   bool ok = true;
 
   if (wg == kWgs) {
-    // ================= MMA warps: warp 16+w serves compute warpgroup w.  It sleeps on the stage's fill
-    // barrier (mbarrier.try_wait suspends in hardware), issues the 3xTF32 MMAs of the stage and commits to
-    // the stage's free barrier; the last stage's commit also tells the warpgroup its accumulator is complete.
+    // ================= MMA warps: warp 16+w serves compute warpgroup w.  It sleeps on the stage's fill barrier —
+    // a named hardware barrier (bar.sync; the compute warps bar.arrive), so a waiting MMA warp issues nothing:
+    // polling an mbarrier here cost 15 % of the SM's issue slots — issues the 3xTF32 MMAs of the stage and
+    // commits to the stage's free barrier; the last stage's commit also tells the warpgroup its accumulator is
+    // complete.
     const int w = wwarp;
-    if (lane == 0) {
-      uint32_t fills0 = 0, fills1 = 0;
-      const uint32_t a_wg = nws_smem_u32(smem + C::oA + w * 4 * C::kStageBytes);
-      const uint32_t acc = tmem_base_s + w * 64;
-      bool more = true;
-      while (more && ok) {   // one iteration per tile of warpgroup w; tiles are handed out dynamically
+    const uint32_t a_wg = nws_smem_u32(smem + C::oA + w * 4 * C::kStageBytes);
+    const uint32_t acc = tmem_base_s + w * 64;
+    bool more = true;
+    while (more) {   // one iteration per tile of warpgroup w; tiles are handed out dynamically
 #pragma unroll 1
-        for (int st = 0; st < C::NST && ok; ++st) {
-          const int buf = st & 1;
-          const uint32_t par = (buf ? fills1 : fills0) & 1;
-          uint32_t spins = 0;
-          while (!nws_mbar_try_wait(&fill_bar[w][buf], par)) {
-            if (st == 0 && done_s[w]) { more = false; break; }   // the warpgroup found no further tile
-            if (++spins > (1u << 26)) { ok = false; break; }
-          }
-          if (!more || !ok) break;
-          nws_tc_fence_after();
+      for (int st = 0; st < C::NST; ++st) {
+        const int buf = st & 1;
+        fill_wait(w, buf);
+        if (st == 0 && done_s[w]) { more = false; break; }   // woken by the warpgroup running out of tiles
+        nws_tc_fence_after();
+        if (lane == 0) {
           const int k0 = st * C::KS;
           const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;
           const uint32_t a_hi = a_wg + buf * 2 * C::kStageBytes, a_lo = a_hi + C::kStageBytes;
@@ -175,8 +173,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
             nws_umma_tf32(acc, dah, dbl, idesc, 1u);
           }
           nws_umma_commit(&free_bar[w][buf]);
-          if (buf) ++fills1; else ++fills0;
         }
+        __syncwarp();
       }
     }
   } else
@@ -303,10 +301,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       }
       nws_fence_proxy_async();   // operand stores -> visible to the tensor core's async proxy
       nws_tc_fence_before();     // (first stage) this thread's TMEM reads of the previous tile are ordered too
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nws_smem_u32(&fill_bar[wg][buf])) : "memory");
-      }
+      fill_arrive(wg, buf);
       if (buf) ++uses1; else ++uses0;
     }
     {  // accumulator complete when the last stage's commit lands (a commit covers all earlier MMAs)
@@ -360,6 +355,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     if (wt == 0) tile_s[wg] = next_tile;   // ordered before the readers by the barrier at the top of the loop
   }
   if (wt == 0) done_s[wg] = 1;
+  fill_arrive(wg, 0);   // the MMA warp is waiting for stage 0 of a tile that will not come
   }
   if (!ok && fault) atomicExch(fault, 1);
   nws_tc_fence_before();

@@ -118,6 +118,23 @@ NWS_HD float nws_sinf_fast(float x) {
 #endif
 }
 
+// SFU sine with a full-turn reduction: q = rint(x / 2pi) by the same magic-number trick, r = x - q*2pi in two
+// FMAs (2pi = C1 + C2, |r| <= pi), one MUFU.SIN.  No quadrant select, half the SFU work of nws_sinf_fast;
+// the reduction rounds at |r| ~ pi instead of pi/4, so the worst case is a little looser (measured by
+// nws_selftest_sin, tests/test_gpu_parity.py::test_sin_variants).  Valid for |x| < 2^22 * 2pi = 2.6e7 rad.
+NWS_HD float nws_sinf_turn(float x) {
+  const float magic = 12582912.0f;  // 1.5 * 2^23
+  const float t = NWS_FMA(x, 0.15915494309189533577f, magic);
+  const float q = NWS_ADD(t, -magic);
+  float r = NWS_FMA(-q, 6.28318548202514648438f, x);       // C1 = fp32(2pi)
+  r = NWS_FMA(-q, -1.7484556000744883e-07f, r);            // C2 = 2pi - C1
+#if defined(__CUDA_ARCH__)
+  return __sinf(r);
+#else
+  return sinf(r);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // FastNEWT index arithmetic (shaping.py:137-146), bit-exact with torch CPU:
 //   idx = (table_size * (x - table_min)) / (table_max - table_min)      [fp32 sub, mul, TRUE division]

@@ -85,7 +85,7 @@ __global__ void nws_selftest_sin_kernel(const float* __restrict__ x, float* __re
   if (i >= n) return;
   y_acc[i] = nws_sinf(x[i]);
   y_fast3[i] = nws_sinf_fast<3>(x[i]);
-  y_fast2[i] = nws_sinf_fast<2>(x[i]);
+  y_fast2[i] = nws_sinf_turn(x[i]);
 }
 
 extern "C" int nws_selftest_sin(const float* x, float* y_acc, float* y_fast3, float* y_fast2, long long n, void* stream) {

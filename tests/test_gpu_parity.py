@@ -97,16 +97,16 @@ def test_sin_variants():
     xs = torch.cat([(torch.rand(400000, generator=g) * 2 - 1) * 1.2e6, (torch.rand(400000, generator=g) * 2 - 1) * 2e5,
                     (torch.rand(200000, generator=g) * 2 - 1) * 1300, (torch.rand(200000, generator=g) * 2 - 1) * 120,
                     (torch.rand(200000, generator=g) * 2 - 1) * 4]).cuda()
-    ya, y3, y2 = torch.empty_like(xs), torch.empty_like(xs), torch.empty_like(xs)
-    assert lib.nws_selftest_sin(xs.data_ptr(), ya.data_ptr(), y3.data_ptr(), y2.data_ptr(), xs.numel(), None) == 0
+    ya, yq, yt = torch.empty_like(xs), torch.empty_like(xs), torch.empty_like(xs)
+    assert lib.nws_selftest_sin(xs.data_ptr(), ya.data_ptr(), yq.data_ptr(), yt.data_ptr(), xs.numel(), None) == 0
     ref = torch.sin(xs.double())
     ea = (ya.double() - ref).abs().max().item()
-    e3 = (y3.double() - ref).abs().max().item()
-    small = xs.abs() < 1300
-    e2 = (y2.double() - ref)[small].abs().max().item()
-    print("sin max abs err: accurate %.3e  fast3 %.3e  fast2(|x|<1300) %.3e" % (ea, e3, e2))
+    eq = (yq.double() - ref).abs().max().item()
+    et = (yt.double() - ref).abs()
+    print("sin max abs err: accurate %.3e  quarter-turn SFU %.3e  full-turn SFU %.3e (rms %.3e)" %
+          (ea, eq, et.max().item(), et.pow(2).mean().sqrt().item()))
     assert ea < 1.5e-7
-    assert e3 < 6e-7 and e2 < 6e-7
+    assert eq < 6e-7 and et.max().item() < 1e-6 and et.pow(2).mean().sqrt().item() < 2.5e-7
 
 
 @pytest.mark.parametrize("impl", [1, 0])   # 1 = tcgen05 MLP chain (default), 0 = fp32 SIMT layers
