@@ -200,7 +200,9 @@ int nws_set_mlp_impl(NwsHandle handle, int impl);
 int nws_set_audio_impl(NwsHandle handle, int impl);
 
 /* Self-test of the tcgen05 path (csrc/nws_tc.cuh): D[128,64] = A[128,K] . B[64,K]^T, 3xTF32 in TMEM,
- * K a multiple of 8 up to 104.  status[0] = 1 on completion, -1 if the MMA never signalled. */
+ * K a multiple of 8 up to 104.  status[0] = 1 on completion, -1 if the MMA never signalled.
+ * swap_lbo_sbo bit 0: exchange the descriptor strides (negative test); bit 1: store A's low part without
+ * masking it to tf32 (the result must not change: kind::tf32 ignores the 13 low mantissa bits). */
 int nws_selftest_umma(const float* A, const float* B, float* D, int K, int swap_lbo_sbo, int* status, void* stream);
 
 /* Accuracy probe of the device sine implementations (csrc/nws_math.h): accurate polynomial version and

@@ -88,7 +88,7 @@ __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <bool USE_LUT, bool TAP, int MLP_MODE>
+template <bool USE_LUT, bool TAP, int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAudioParams p, const float* __restrict__ w_umma,
                                                                      int* __restrict__ fault) {
   using C = TcCfg<USE_LUT>;
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
               const float kf = k0f + (float)(kk + j + 1);
               const float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL(kf, phase), sm_shift[k0 + kk + j]));   // generators.py:60-61
               h[j] = nws_tf32_hi(s);
-              l[j] = nws_tf32_lo(s, h[j]);
+              l[j] = s - h[j];   // exact; the tensor core ignores the 13 low bits (nws_selftest_umma checks)
             }
             const uint32_t off = (kk >> 2) * kLboA + wt * 16;   // chunk kk/4, row wt: conflict-free 16 B per thread
             *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
               float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL(kf, phase), sm_shift[k0 + kk + j]));
               s = NWS_MUL(f0u, kf) < 0.5f * kSampleRate ? s : 0.f;
               h[j] = nws_tf32_hi(s);
-              l[j] = nws_tf32_lo(s, h[j]);
+              l[j] = s - h[j];   // exact; the tensor core ignores the 13 low bits (nws_selftest_umma checks)
             }
             const uint32_t off = (kk >> 2) * kLboA + wt * 16;
             *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
@@ -314,14 +314,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     // ---- FiLM -> shaper -> FiLM -> mixdown (shaping.py:67-79), exciter read from this thread's TMEM lane
     const float4* cf = reinterpret_cast<const float4*>(sm_coef + (wt >> 6) * kShapers * 8);
     const float l1 = lc.l1;
-    const int lut_size = p.lut_size;
+    // FastNEWT: MODE 2 = the table size is the reference's default 4096 (shaping.py:101), known at compile time
+    // so a row offset is an immediate; MODE 1 = any size.  Offsets are 32-bit (a table is < 4 GB).
+    const int lut_size = (USE_LUT && MODE == 2) ? 4096 : p.lut_size;
+    const float lut_size_f = (float)lut_size;
     const float lut_min = p.lut_min, lut_span = p.lut_span, lut_rcp = p.lut_span_rcp;
+    const char* lut_bytes = reinterpret_cast<const char*>(p.lut2);
     float mix = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < kShapers; c0 += C::kChPerLd) {
       float ev[C::kChPerLd];
       tmem_ld<C::kChPerLd>(tmem_lane + c0, ev);
-      const float2* row = p.lut2 + (size_t)c0 * lut_size;
+      const uint32_t row0 = (uint32_t)(c0 * lut_size);
 #pragma unroll
       for (int i = 0; i < C::kChPerLd; ++i) {
         const int c = c0 + i;
@@ -334,15 +338,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
         const float x = NWS_ADD(NWS_MUL(g_i, e), b_i);
         float y;
         if (USE_LUT) {
-          // FastNEWT.shaping_fn (shaping.py:136-151): same index arithmetic as nws_lut_index; the table row
-          // holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
-          const float idx = nws_div_markstein(NWS_MUL((float)lut_size, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
-          float fl = floorf(idx);
-          fl = fminf(fmaxf(fl, 0.0f), (float)(lut_size - 1));
-          const float2 t2 = __ldg(row + (size_t)i * lut_size + (int)fl);
-          y = NWS_ADD(NWS_MUL(t2.y, NWS_ADD(idx, -fl)), t2.x);
+          // FastNEWT.shaping_fn (shaping.py:136-151): same index arithmetic as nws_lut_index — floor and clamp
+          // done on the integer side (F2I.FLOOR saturates, NaN -> 0 with a NaN fract, as floorf/fmaxf/fminf give);
+          // the table row holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
+          const float idx = nws_div_markstein(NWS_MUL(lut_size_f, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
+          int fi = __float2int_rd(idx);
+          fi = min(max(fi, 0), lut_size - 1);
+          const uint32_t off = (row0 + (uint32_t)(i * lut_size) + (uint32_t)fi) * 8u;
+          const float2 t2 = __ldg(reinterpret_cast<const float2*>(lut_bytes + off));
+          y = NWS_ADD(NWS_MUL(t2.y, NWS_ADD(idx, -(float)fi)), t2.x);
         } else {
-          y = nws_shaper_mlp<MLP_MODE>(sm_shaper + c * kShaperStride, x);
+          y = nws_shaper_mlp<MODE>(sm_shaper + c * kShaperStride, x);
         }
         const float z = NWS_ADD(NWS_MUL(g_n, y), b_n);
         mix = fmaf(bw.y, z, mix);
@@ -383,6 +389,7 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   static bool attr_done[64] = {};
   if (nws_first_use_on_device(attr_done)) {
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
@@ -395,7 +402,8 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   const int grid = (int)(want < cap ? want : cap);
   const float* wu = w + ctx->lay.hmix_umma;
   const bool direct = ctx->shaper_inner_bound <= 8.0f;   // see NWS_SHAPER_SIN_INNER
-  if (use_lut && !exciter_out) nws_audio_tc_kernel<true, false, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
+  if (use_lut && !exciter_out && ctx->lut_size == 4096) nws_audio_tc_kernel<true, false, 2><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
+  else if (use_lut && !exciter_out) nws_audio_tc_kernel<true, false, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
   else if (use_lut) nws_audio_tc_kernel<true, true, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
   else if (!exciter_out && direct) nws_audio_tc_kernel<false, false, 2><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
   else if (!exciter_out) nws_audio_tc_kernel<false, false, 1><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);

@@ -10,6 +10,8 @@ __global__ void __launch_bounds__(128) nws_selftest_umma_kernel(const float* __r
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool raw_lo = (swap & 2) != 0;   // A's low part stored unmasked: the tensor core must ignore the 13 low bits
+  swap &= 1;
   const uint32_t a_bytes = 128 * K * 4, b_bytes = 64 * K * 4;
   unsigned char* a_hi = smem_raw;
   unsigned char* a_lo = a_hi + a_bytes;
@@ -19,7 +21,7 @@ __global__ void __launch_bounds__(128) nws_selftest_umma_kernel(const float* __r
   for (int k = 0; k < K; ++k) {
     const float a = A[tid * K + k], h = nws_tf32_hi(a);
     *reinterpret_cast<float*>(a_hi + nws_umma_offset(tid, k, 128)) = h;
-    *reinterpret_cast<float*>(a_lo + nws_umma_offset(tid, k, 128)) = nws_tf32_lo(a, h);
+    *reinterpret_cast<float*>(a_lo + nws_umma_offset(tid, k, 128)) = raw_lo ? a - h : nws_tf32_lo(a, h);
     if (tid < 64) {
       const float b = B[tid * K + k], hb = nws_tf32_hi(b);
       *reinterpret_cast<float*>(b_hi + nws_umma_offset(tid, k, 64)) = hb;

@@ -86,6 +86,12 @@ def test_tcgen05_selftest():
         assert int(st[0]) == 1
         ref = A.double() @ B.double().t()
         assert (D.double() - ref).abs().max().item() < 4e-6
+        # kind::tf32 reads the top 19 bits of each fp32 operand word: an unmasked low part gives the same bits
+        # (the fused audio kernel relies on this to skip one LOP3 per harmonic)
+        D2 = torch.zeros(128, 64, device="cuda")
+        assert lib.nws_selftest_umma(A.data_ptr(), B.data_ptr(), D2.data_ptr(), K, 2, st.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        assert int(st[0]) == 1 and torch.equal(D, D2)
 
 
 def test_sin_variants():
