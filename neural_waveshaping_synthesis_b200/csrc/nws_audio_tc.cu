@@ -59,6 +59,13 @@ __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 
 __device__ __forceinline__ void fill_arrive(int wg, int buf) { asm volatile("bar.arrive %0, 160;" ::"r"(5 + 2 * wg + buf) : "memory"); }
 __device__ __forceinline__ void fill_wait(int wg, int buf) { asm volatile("bar.sync %0, 160;" ::"r"(5 + 2 * wg + buf) : "memory"); }
 
+// max(min(a, b), 0) in one instruction
+__device__ __forceinline__ int nws_min_relu(int a, int b) {
+  int d;
+  asm("min.s32.relu %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
 template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
 template <>
@@ -95,6 +102,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t free_bar[kWgs][2];   // the MMAs that read the stage have completed (tcgen05.commit)
   __shared__ double warp_tot[kWgs + 1][4];
+  __shared__ float2 film_k[kWgs][4];       // per (warpgroup, warp): partial sums of w_c*(Ab_n, Db_n) over the warp's 32 channels
   __shared__ uint32_t tmem_base_s;
   __shared__ int tile_s[kWgs];              // tile handed to each warpgroup by the dynamic scheduler
   __shared__ volatile int done_s[kWgs];     // warpgroup has run out of tiles (tells its MMA warp to stop)
@@ -218,23 +226,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     const float phase = nws_phase_from_cumsum(csum, (float)kSampleRate);
     {
       // FiLM upsample (shaping.py:69) as A + l1*(B - A): every sample of a half-hop blends the same two
-      // frames, so the per-channel pairs (A, B-A) of the four FiLM parameters are tabulated once per tile
-      // (thread = (half, channel)); the film frames were published by the barrier above
+      // frames, so per (half, channel) the tile tabulates everything that does not depend on the sample
+      // (thread = (half, channel); the film frames were published by the barrier above).  With g = Ag + l1*Dg,
+      // b = Ab + l1*Db and the exciter e = acc + bias (harmonic_mixer bias, neural_waveshaping.py:54):
+      //   FiLM in   x = g_i*e + b_i      = fma(l1, fma(Dg, acc, Db'), fma(Ag, acc, Ab'))     Ab' = Ag*bias + Ab, Db' likewise
+      //   FiLM out + mixdown (shaping.py:76-79)  sum_c w_c*(g_n*y_c + b_n)
+      //                                  = sum_c Agw*y_c + l1 * sum_c Dgw*y_c + (KA + l1*KD)     Agw = w_c*Ag_n, KA = sum_c w_c*Ab_n
+      // so the per-channel loop costs 3 + 2 FMAs instead of 4 lerps + 2 mul/add pairs + 1 FMA.
       const int h = wt >> 6, c = wt & 63;
       const int sa = h == 0 ? (t >= 1 ? 0 : 1) : 1;
       const int sb = h == 0 ? (t >= 1 ? 1 : 2) : (t + 1 < T ? 2 : 1);
       const float* fa = sm_film + sa * kFilm + c;
       const float* fb = sm_film + sb * kFilm + c;
+      const float2 bw = sm_bw[c];
       float4 lo4, hi4;
       lo4.x = fa[0]; lo4.y = fb[0] - fa[0];
-      lo4.z = fa[kShapers]; lo4.w = fb[kShapers] - fa[kShapers];
-      hi4.x = fa[2 * kShapers]; hi4.y = fb[2 * kShapers] - fa[2 * kShapers];
-      hi4.z = fa[3 * kShapers]; hi4.w = fb[3 * kShapers] - fa[3 * kShapers];
+      lo4.z = fmaf(lo4.x, bw.x, fa[kShapers]); lo4.w = fmaf(lo4.y, bw.x, fb[kShapers] - fa[kShapers]);
+      hi4.x = bw.y * fa[2 * kShapers]; hi4.y = bw.y * (fb[2 * kShapers] - fa[2 * kShapers]);
+      hi4.z = 0.f; hi4.w = 0.f;
+      float ka = bw.y * fa[3 * kShapers], kd = bw.y * (fb[3 * kShapers] - fa[3 * kShapers]);
       float4* dst = reinterpret_cast<float4*>(sm_coef + (h * kShapers + c) * 8);
       dst[0] = lo4;
       dst[1] = hi4;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ka += __shfl_xor_sync(0xffffffffu, ka, o);
+        kd += __shfl_xor_sync(0xffffffffu, kd, o);
+      }
+      if (lane == 0) film_k[wg][wwarp] = make_float2(ka, kd);
     }
     wg_barrier(wg);   // coefficient table visible to the whole warpgroup before the shaper loop reads it
+    float mix_ka, mix_kd;   // this half-hop's constant part of the mixdown
+    {
+      const float2 ka0 = film_k[wg][(wt >> 6) * 2], ka1 = film_k[wg][(wt >> 6) * 2 + 1];
+      mix_ka = ka0.x + ka1.x;
+      mix_kd = ka0.y + ka1.y;
+    }
 
     // ---- oscillator bank -> A operand stages -> tcgen05.mma
 #pragma unroll 1
@@ -319,43 +346,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     const int lut_size = (USE_LUT && MODE == 2) ? 4096 : p.lut_size;
     const float lut_size_f = (float)lut_size;
     const float lut_min = p.lut_min, lut_span = p.lut_span, lut_rcp = p.lut_span_rcp;
-    const char* lut_bytes = reinterpret_cast<const char*>(p.lut2);
-    float mix = 0.f;
+    float mix_a = 0.f, mix_d = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < kShapers; c0 += C::kChPerLd) {
       float ev[C::kChPerLd];
       tmem_ld<C::kChPerLd>(tmem_lane + c0, ev);
-      const uint32_t row0 = (uint32_t)(c0 * lut_size);
+      // row pointer of channel c0: the rows of the other channels of the group are immediates of the load
+      const float2* lut_row = p.lut2 + (size_t)(c0 * lut_size);
+      asm("" : "+l"(lut_row));   // keep the row pointer a 64-bit value of its own: per channel one IMAD.WIDE + load
 #pragma unroll
       for (int i = 0; i < C::kChPerLd; ++i) {
         const int c = c0 + i;
-        const float2 bw = sm_bw[c];
-        const float e = ev[i] + bw.x;
-        if (TAP) p.exciter_out[((size_t)b * kShapers + c) * N + n] = e;
-        const float4 ci = cf[2 * c], cn = cf[2 * c + 1];
-        const float g_i = fmaf(l1, ci.y, ci.x), b_i = fmaf(l1, ci.w, ci.z);
-        const float g_n = fmaf(l1, cn.y, cn.x), b_n = fmaf(l1, cn.w, cn.z);
-        const float x = NWS_ADD(NWS_MUL(g_i, e), b_i);
+        if (TAP) p.exciter_out[((size_t)b * kShapers + c) * N + n] = ev[i] + sm_bw[c].x;
+        const float4 ci = cf[2 * c];
+        const float2 cn = *reinterpret_cast<const float2*>(&cf[2 * c + 1]);
+        const float x = fmaf(l1, fmaf(ci.y, ev[i], ci.w), fmaf(ci.x, ev[i], ci.z));
         float y;
         if (USE_LUT) {
           // FastNEWT.shaping_fn (shaping.py:136-151): same index arithmetic as nws_lut_index — floor and clamp
           // done on the integer side (F2I.FLOOR saturates, NaN -> 0 with a NaN fract, as floorf/fmaxf/fminf give);
           // the table row holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
           const float idx = nws_div_markstein(NWS_MUL(lut_size_f, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
-          int fi = __float2int_rd(idx);
-          fi = min(max(fi, 0), lut_size - 1);
-          const uint32_t off = (row0 + (uint32_t)(i * lut_size) + (uint32_t)fi) * 8u;
-          const float2 t2 = __ldg(reinterpret_cast<const float2*>(lut_bytes + off));
-          y = NWS_ADD(NWS_MUL(t2.y, NWS_ADD(idx, -(float)fi)), t2.x);
+          const int fi = nws_min_relu(__float2int_rd(idx), lut_size - 1);   // clamp to [0, size-1]: one VIMNMX.RELU
+          const float2 t2 = __ldg(lut_row + i * lut_size + (uint32_t)fi);
+          y = fmaf(t2.y, NWS_ADD(idx, -(float)fi), t2.x);
         } else {
           y = nws_shaper_mlp<MODE>(sm_shaper + c * kShaperStride, x);
         }
-        const float z = NWS_ADD(NWS_MUL(g_n, y), b_n);
-        mix = fmaf(bw.y, z, mix);
+        mix_a = fmaf(cn.x, y, mix_a);
+        mix_d = fmaf(cn.y, y, mix_d);
       }
     }
     nws_tc_fence_before();   // TMEM reads ordered before the next tile's first MMA (via the warpgroup barrier)
-    float o = mix + mix_b;
+    float o = fmaf(l1, mix_d + mix_kd, mix_a + mix_ka) + mix_b;
     o += noise_v;
     p.out[(size_t)b * N + n] = ok ? o : __int_as_float(0x7fc00000);
     if (wt == 0) tile_s[wg] = next_tile;   // ordered before the readers by the barrier at the top of the loop
