@@ -59,6 +59,12 @@ __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 
 __device__ __forceinline__ void fill_arrive(int wg, int buf) { asm volatile("bar.arrive %0, 160;" ::"r"(5 + 2 * wg + buf) : "memory"); }
 __device__ __forceinline__ void fill_wait(int wg, int buf) { asm volatile("bar.sync %0, 160;" ::"r"(5 + 2 * wg + buf) : "memory"); }
 
+__device__ __forceinline__ void nws_cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(nws_smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void nws_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void nws_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // max(min(a, b), 0) in one instruction
 __device__ __forceinline__ int nws_min_relu(int a, int b) {
   int d;
@@ -104,7 +110,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   __shared__ double warp_tot[kWgs + 1][4];
   __shared__ float2 film_k[kWgs][4];       // per (warpgroup, warp): partial sums of w_c*(Ab_n, Db_n) over the warp's 32 channels
   __shared__ uint32_t tmem_base_s;
-  __shared__ int tile_s[kWgs];              // tile handed to each warpgroup by the dynamic scheduler
+  __shared__ int tile_s[kWgs][2];           // next tile of each warpgroup (dynamic scheduler), two slots used alternately
   __shared__ volatile int done_s[kWgs];     // warpgroup has run out of tiles (tells its MMA warp to stop)
 
   const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, lane = tid & 31, wwarp = wt >> 5;
@@ -189,28 +195,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   {
   // dynamic tile scheduler: tiles (utterance b, hop t) are claimed from a global counter, so CTAs that start
   // late (SMs still busy with the encoder of a later time block) do not hold tiles hostage
-  if (wt == 0) tile_s[wg] = atomicAdd(p.tile_counter, 1);
-  int next_tile = 0;
-  for (;;) {
-    wg_barrier(wg);   // previous tile: film / coefficient table / warp_tot no longer read; tile_s published
-    const long long tile = tile_s[wg];
-    if (tile >= n_tiles) break;
-    if (wt == 0) next_tile = atomicAdd(p.tile_counter, 1);   // claimed now, needed a whole tile later
-    const int b = (int)(tile / hops), t = p.t_begin + (int)(tile - (long long)b * hops);
+  // The three FiLM frames a tile blends (t-1, t, t+1; 3 KB) are fetched by cp.async one tile ahead: the film
+  // buffer is dead once the coefficient table is built, so the next tile's rows stream into it while this
+  // tile's oscillator bank and shaper loop run.
+  auto film_prefetch = [&](long long tl) {
+    const int pb = (int)(tl / hops), pt = p.t_begin + (int)(tl - (long long)pb * hops);
     for (int i = wt; i < 3 * kFilm / 4; i += 128) {
-      const int slot = i / (kFilm / 4), fr = t - 1 + slot;
+      const int slot = i / (kFilm / 4), fr = pt - 1 + slot;
       if (fr >= 0 && fr < T)
-        reinterpret_cast<float4*>(sm_film)[i] =
-            reinterpret_cast<const float4*>(p.film + ((size_t)b * T + fr) * kFilm)[i - slot * (kFilm / 4)];
+        nws_cp_async16(reinterpret_cast<float4*>(sm_film) + i,
+                       reinterpret_cast<const float4*>(p.film + ((size_t)pb * T + fr) * kFilm) + (i - slot * (kFilm / 4)));
     }
+    nws_cp_async_commit();
+  };
+  // Thread 0 of the warpgroup claims tiles two ahead, so the atomic's round trip is never waited for.
+  int claimed = 0;
+  if (wt == 0) {
+    tile_s[wg][0] = atomicAdd(p.tile_counter, 1);
+    claimed = atomicAdd(p.tile_counter, 1);
+  }
+  wg_barrier(wg);
+  long long tile = tile_s[wg][0];
+  if (tile < n_tiles) film_prefetch(tile);
+  int par = 0;
+  for (;;) {
+    if (tile >= n_tiles) break;
+    if (wt == 0) {
+      tile_s[wg][par ^ 1] = claimed;                  // the next tile: published by the scan barrier below
+      claimed = atomicAdd(p.tile_counter, 1);         // the one after
+    }
+    const int b = (int)(tile / hops), t = p.t_begin + (int)(tile - (long long)b * hops);
     // ---- f0 upsample and the cumsum of generators.py:59 (fp64 scan + per-hop carry)
     const int n = t * kHop + wt;
     const NwsLerp lc = nws_lerp_coords(n, T, inv_hop);
     const float* f0b = p.f0 + (size_t)b * T;
-    // issued early so their latency hides behind the scan / the whole tile: the hop's fp64 phase carry and the
-    // noise-branch sample that is added to the mixdown at the very end
+    // issued early so its latency hides behind the scan: the hop's fp64 phase carry
     const double carry_v = p.carry[(size_t)b * T + t];
-    const float noise_v = p.noise_in ? p.noise_in[(size_t)b * N + n] : 0.f;   // (aliases p.out: plain load)
     const float f0u = nws_lerp_apply(lc, f0b[lc.i0], f0b[lc.i1]);
     double v = (double)f0u;
 #pragma unroll
@@ -219,7 +239,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       if (lane >= o) v += u;
     }
     if (lane == 31) warp_tot[wg][wwarp] = v;
-    wg_barrier(wg);
+    nws_cp_async_wait_all();   // this thread's share of the tile's film rows has landed ...
+    wg_barrier(wg);            // ... and everybody's is visible, with the warp totals and the next tile
     double pre = carry_v;
     for (int w = 0; w < wwarp; ++w) pre += warp_tot[wg][w];
     const float csum = (float)(pre + v);
@@ -255,7 +276,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       }
       if (lane == 0) film_k[wg][wwarp] = make_float2(ka, kd);
     }
-    wg_barrier(wg);   // coefficient table visible to the whole warpgroup before the shaper loop reads it
+    wg_barrier(wg);   // coefficient table visible to the whole warpgroup before the shaper loop reads it; film rows dead
+    const long long tile_next = tile_s[wg][par ^ 1];
+    if (tile_next < n_tiles) film_prefetch(tile_next);
     float mix_ka, mix_kd;   // this half-hop's constant part of the mixdown
     {
       const float2 ka0 = film_k[wg][(wt >> 6) * 2], ka1 = film_k[wg][(wt >> 6) * 2 + 1];
@@ -331,6 +354,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       fill_arrive(wg, buf);
       if (buf) ++uses1; else ++uses0;
     }
+    // the noise-branch sample that is added to the mixdown at the very end: its latency hides behind the shaper loop
+    const float noise_v = p.noise_in ? p.noise_in[(size_t)b * N + n] : 0.f;   // (aliases p.out: plain load)
     {  // accumulator complete when the last stage's commit lands (a commit covers all earlier MMAs)
       const int lb = (C::NST - 1) & 1;
       const uint32_t u = lb ? uses1 : uses0;
@@ -381,7 +406,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     float o = fmaf(l1, mix_d + mix_kd, mix_a + mix_ka) + mix_b;
     o += noise_v;
     p.out[(size_t)b * N + n] = ok ? o : __int_as_float(0x7fc00000);
-    if (wt == 0) tile_s[wg] = next_tile;   // ordered before the readers by the barrier at the top of the loop
+    tile = tile_next;
+    par ^= 1;
   }
   if (wt == 0) done_s[wg] = 1;
   fill_arrive(wg, 0);   // the MMA warp is waiting for stage 0 of a tile that will not come
