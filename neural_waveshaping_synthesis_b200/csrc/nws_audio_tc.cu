@@ -35,18 +35,19 @@ namespace {
 constexpr int kWgs = 4;                  // compute warpgroups per CTA
 constexpr int kTcThreads = kWgs * 128 + kWgs * 32;   // + one MMA-issuing warp per compute warpgroup
 constexpr int kWBytes = kHarmPad * kShapers * 4;       // one tf32 part of the B operand (26,624 B)
-constexpr uint32_t kLboA = 16 * 128, kLboB = 8 * 128, kSbo = 128;
+constexpr uint32_t kLboB = 8 * 128, kSbo = 128;
 
 template <bool USE_LUT>
 struct TcCfg {
   static constexpr int KS = USE_LUT ? 16 : 8;                 // harmonics per A stage
   static constexpr int NST = (kHarmPad + KS - 1) / KS;        // stages per tile (7 or 13)
-  static constexpr int kStageBytes = 128 * KS * 4;            // one tf32 part of one stage
+  // tensor-memory columns of one warpgroup: accumulator [0,64) | A stage buffer 0: hi KS, lo KS | buffer 1: hi KS, lo KS
+  static constexpr uint32_t kColA = kShapers;
+  static constexpr uint32_t kTmemColsWg = 128;
   static constexpr int kChPerLd = USE_LUT ? 8 : 2;            // exciter channels per TMEM load
   // dynamic shared memory layout (bytes)
   static constexpr int oW = 0;                                // W_hi | W_lo
-  static constexpr int oA = oW + 2 * kWBytes;                 // [wg][stage][hi|lo]
-  static constexpr int oFilm = oA + kWgs * 2 * 2 * kStageBytes;  // [wg][3][256] floats
+  static constexpr int oFilm = oW + 2 * kWBytes;              // [wg][3][256] floats
   static constexpr int oCoef = oFilm + kWgs * 3 * kFilm * 4;     // [wg][half][64][8] floats: FiLM lerp coefficients
   static constexpr int oSmall = oCoef + kWgs * 2 * kShapers * 8 * 4;  // hmix_b[64] | shift[104] | mix_w[64] floats
   static constexpr int oShaper = oSmall + (kShapers + kHarmPad + kShapers) * 4;
@@ -58,6 +59,25 @@ __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 
 // (non-blocking; their shared-memory stores are ordered before the consumer's wake-up), the MMA warp syncs.
 __device__ __forceinline__ void fill_arrive(int wg, int buf) { asm volatile("bar.arrive %0, 160;" ::"r"(5 + 2 * wg + buf) : "memory"); }
 __device__ __forceinline__ void fill_wait(int wg, int buf) { asm volatile("bar.sync %0, 160;" ::"r"(5 + 2 * wg + buf) : "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, one thread issues
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// this thread's lane, 8 consecutive columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void nws_cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(nws_smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -121,7 +141,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   float* sm_film = reinterpret_cast<float*>(smem + C::oFilm) + (wg & 3) * 3 * kFilm;
   float* sm_coef = reinterpret_cast<float*>(smem + C::oCoef) + (wg & 3) * 2 * kShapers * 8;
   float* sm_shaper = reinterpret_cast<float*>(smem + C::oShaper);
-  unsigned char* a_base = smem + C::oA + (wg & 3) * 4 * C::kStageBytes;   // [stage][hi|lo]
 
   // ---- CTA-lifetime staging
   for (int i = tid; i < 2 * kWBytes / 16; i += kTcThreads)
@@ -132,7 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     for (int i = tid; i < kShapers * kShaperStride / 4; i += kTcThreads)
       reinterpret_cast<float4*>(sm_shaper)[i] = reinterpret_cast<const float4*>(p.shaper)[i];
   if (tid < kWgs) done_s[tid] = 0;
-  if (tid < 32) nws_tmem_alloc(&tmem_base_s, 64 * kWgs);
+  if (tid < 32) nws_tmem_alloc(&tmem_base_s, C::kTmemColsWg * kWgs);
   if (tid == 0) {
     for (int i = 0; i < kWgs * 2; ++i) {
       nws_mbar_init(&free_bar[0][0] + i, 1);
@@ -143,11 +162,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   nws_tc_fence_before();
   __syncthreads();
   nws_tc_fence_after();
-  const uint32_t tmem_acc = tmem_base_s + (wg & 3) * 64;                 // this warpgroup's 64 columns
+  const uint32_t tmem_acc = tmem_base_s + (wg & 3) * C::kTmemColsWg;     // this warpgroup's columns
   const uint32_t tmem_lane = tmem_acc + ((uint32_t)(wwarp * 32) << 16);   // this warp's lane quarter
   const uint32_t idesc = nws_umma_idesc_tf32(128, 64);
   const uint32_t w_hi_addr = nws_smem_u32(smem + C::oW), w_lo_addr = w_hi_addr + kWBytes;
-  const uint32_t a_addr = nws_smem_u32(a_base);
   const float mix_b = p.mix_b[0];
   const float inv_hop = (float)T / (float)N;
   const int hops = p.t_end - p.t_begin;
@@ -162,8 +180,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     // commits to the stage's free barrier; the last stage's commit also tells the warpgroup its accumulator is
     // complete.
     const int w = wwarp;
-    const uint32_t a_wg = nws_smem_u32(smem + C::oA + w * 4 * C::kStageBytes);
-    const uint32_t acc = tmem_base_s + w * 64;
+    const uint32_t acc = tmem_base_s + w * C::kTmemColsWg;
     bool more = true;
     while (more) {   // one iteration per tile of warpgroup w; tiles are handed out dynamically
 #pragma unroll 1
@@ -175,16 +192,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
         if (lane == 0) {
           const int k0 = st * C::KS;
           const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;
-          const uint32_t a_hi = a_wg + buf * 2 * C::kStageBytes, a_lo = a_hi + C::kStageBytes;
+          const uint32_t a_hi = acc + C::kColA + buf * 2 * C::KS, a_lo = a_hi + C::KS;   // A operand: tensor memory
           for (int j = 0; j < ks_here / 8; ++j) {
-            const uint64_t dah = nws_umma_smem_desc(a_hi + j * 2 * kLboA, kLboA, kSbo);
-            const uint64_t dal = nws_umma_smem_desc(a_lo + j * 2 * kLboA, kLboA, kSbo);
             const uint32_t wb = (k0 / 4 + 2 * j) * kLboB;
             const uint64_t dbh = nws_umma_smem_desc(w_hi_addr + wb, kLboB, kSbo);
             const uint64_t dbl = nws_umma_smem_desc(w_lo_addr + wb, kLboB, kSbo);
-            nws_umma_tf32(acc, dah, dbh, idesc, (st | j) ? 1u : 0u);
-            nws_umma_tf32(acc, dal, dbh, idesc, 1u);
-            nws_umma_tf32(acc, dah, dbl, idesc, 1u);
+            umma_tf32_ts(acc, a_hi + j * 8, dbh, idesc, (st | j) ? 1u : 0u);
+            umma_tf32_ts(acc, a_lo + j * 8, dbh, idesc, 1u);
+            umma_tf32_ts(acc, a_hi + j * 8, dbl, idesc, 1u);
           }
           nws_umma_commit(&free_bar[w][buf]);
         }
@@ -294,30 +309,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;   // last stage may be short
       const uint32_t prior = buf ? uses1 : uses0;
       if (prior > 0 && ok) ok = nws_mbar_wait(&free_bar[wg][buf], (prior - 1) & 1);   // MMAs that read this buffer are done
-      unsigned char* hi = a_base + buf * 2 * C::kStageBytes;
-      unsigned char* lo = hi + C::kStageBytes;
+      const uint32_t col_hi = tmem_lane + C::kColA + buf * 2 * C::KS, col_lo = col_hi + C::KS;
       // Anti-alias mask (generators.py:50-52): fp32(f0*k) < 8000 is monotone in k for f0 >= 0 and always true
       // for f0 < 0, so one warp vote per stage classifies all 16 harmonics: every lane unmasked (no mask
       // arithmetic), every lane masked (the operand is zero: no sines at all), or mixed (general path).
       const float k_last = k0f + (float)ks_here, k_first = k0f + 1.0f;
       const bool all_on = __all_sync(0xffffffffu, NWS_MUL(f0u, k_last) < 0.5f * kSampleRate && !(f0u != f0u));
       const bool all_off = __all_sync(0xffffffffu, f0u >= 0.f && !(NWS_MUL(f0u, k_first) < 0.5f * kSampleRate));
-      if (all_off) {
+      // eight harmonics (one MMA k-step) at a time: this thread's row of the A operand goes straight to its
+      // tensor-memory lane (tcgen05.st), hi and lo tf32 parts
 #pragma unroll
-        for (int kk = 0; kk < C::KS; kk += 4) {
-          if (kk < ks_here) {
-            const uint32_t off = (kk >> 2) * kLboA + wt * 16;
-            *reinterpret_cast<float4*>(hi + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(lo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      } else if (all_on) {
+      for (int kk = 0; kk < C::KS; kk += 8) {
+        if (kk < ks_here) {
+          float h[8], l[8];
+          if (all_off) {
 #pragma unroll
-        for (int kk = 0; kk < C::KS; kk += 4) {
-          if (kk < ks_here) {
-            float h[4], l[4];
+            for (int j = 0; j < 8; ++j) { h[j] = 0.f; l[j] = 0.f; }
+          } else if (all_on) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
               // harmonic number k = k0 + kk + j + 1 (k0f + const is exact: small integers).  Harmonics 102..104
               // are padding: their mixer weights are zero, so their (finite) sines are never seen.
               const float kf = k0f + (float)(kk + j + 1);
@@ -325,32 +335,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
               h[j] = nws_tf32_hi(s);
               l[j] = s - h[j];   // exact; the tensor core ignores the 13 low bits (nws_selftest_umma checks)
             }
-            const uint32_t off = (kk >> 2) * kLboA + wt * 16;   // chunk kk/4, row wt: conflict-free 16 B per thread
-            *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
-          }
-        }
-      } else {
+          } else {
 #pragma unroll
-        for (int kk = 0; kk < C::KS; kk += 4) {
-          if (kk < ks_here) {
-            float h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const float kf = k0f + (float)(kk + j + 1);
               float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL(kf, phase), sm_shift[k0 + kk + j]));
               s = NWS_MUL(f0u, kf) < 0.5f * kSampleRate ? s : 0.f;
               h[j] = nws_tf32_hi(s);
-              l[j] = s - h[j];   // exact; the tensor core ignores the 13 low bits (nws_selftest_umma checks)
+              l[j] = s - h[j];
             }
-            const uint32_t off = (kk >> 2) * kLboA + wt * 16;
-            *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
           }
+          tmem_st8(col_hi + kk, h);
+          tmem_st8(col_lo + kk, l);
         }
       }
-      nws_fence_proxy_async();   // operand stores -> visible to the tensor core's async proxy
-      nws_tc_fence_before();     // (first stage) this thread's TMEM reads of the previous tile are ordered too
+      tmem_wait_st();            // this thread's operand rows are in tensor memory ...
+      nws_tc_fence_before();     // ... and ordered (with the TMEM reads of the previous tile) before the MMA warp's wake-up
       fill_arrive(wg, buf);
       if (buf) ++uses1; else ++uses0;
     }
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   if (!ok && fault) atomicExch(fault, 1);
   nws_tc_fence_before();
   __syncthreads();
-  if (tid < 32) nws_tmem_dealloc(tmem_base_s, 64 * kWgs);
+  if (tid < 32) nws_tmem_dealloc(tmem_base_s, C::kTmemColsWg * kWgs);
 }
 
 }  // namespace
