@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   const float mix_b = p.mix_b[0];
   const float inv_hop = (float)T / (float)N;
   const int hops = p.t_end - p.t_begin;
-  const long long n_tiles = (long long)p.B * hops;
+  const int n_tiles = p.B * hops;   // < 2^31 (checked by the launcher)
+  const uint32_t hops_magic = p.hops_magic;
   uint32_t uses0 = 0, uses1 = 0;   // fills issued per stage buffer (same in every thread of the warpgroup)
   bool ok = true;
 
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     // complete.
     const int w = wwarp;
     const uint32_t acc = tmem_base_s + w * C::kTmemColsWg;
+    const uint64_t dbh0 = nws_umma_smem_desc(w_hi_addr, kLboB, kSbo), dbl0 = nws_umma_smem_desc(w_lo_addr, kLboB, kSbo);
     bool more = true;
     while (more) {   // one iteration per tile of warpgroup w; tiles are handed out dynamically
 #pragma unroll 1
@@ -194,12 +196,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
           const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;
           const uint32_t a_hi = acc + C::kColA + buf * 2 * C::KS, a_lo = a_hi + C::KS;   // A operand: tensor memory
           for (int j = 0; j < ks_here / 8; ++j) {
-            const uint32_t wb = (k0 / 4 + 2 * j) * kLboB;
-            const uint64_t dbh = nws_umma_smem_desc(w_hi_addr + wb, kLboB, kSbo);
-            const uint64_t dbl = nws_umma_smem_desc(w_lo_addr + wb, kLboB, kSbo);
-            umma_tf32_ts(acc, a_hi + j * 8, dbh, idesc, (st | j) ? 1u : 0u);
-            umma_tf32_ts(acc, a_lo + j * 8, dbh, idesc, 1u);
-            umma_tf32_ts(acc, a_hi + j * 8, dbl, idesc, 1u);
+            // one k-step (8 harmonics) further down the weight tile = 2 * kLboB bytes = +128 in the descriptor's
+            // start-address field (16-byte units; the field cannot carry: shared memory is < 2^18 bytes)
+            const uint64_t adv = (uint64_t)((k0 / 8 + j) * (2 * kLboB / 16));
+            umma_tf32_ts(acc, a_hi + j * 8, dbh0 + adv, idesc, (st | j) ? 1u : 0u);
+            umma_tf32_ts(acc, a_lo + j * 8, dbh0 + adv, idesc, 1u);
+            umma_tf32_ts(acc, a_hi + j * 8, dbl0 + adv, idesc, 1u);
           }
           nws_umma_commit(&free_bar[w][buf]);
         }
@@ -213,8 +215,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   // The three FiLM frames a tile blends (t-1, t, t+1; 3 KB) are fetched by cp.async one tile ahead: the film
   // buffer is dead once the coefficient table is built, so the next tile's rows stream into it while this
   // tile's oscillator bank and shaper loop run.
-  auto film_prefetch = [&](long long tl) {
-    const int pb = (int)(tl / hops), pt = p.t_begin + (int)(tl - (long long)pb * hops);
+  // tile -> (utterance, hop): floor(tile / hops) by a multiply-high with floor(2^32 / hops) and one correction step
+  auto split_tile = [&](int tl, int& ub, int& ut) {
+    int q = (int)__umulhi((uint32_t)tl, hops_magic), r = tl - q * hops;
+    if (r >= hops) { ++q; r -= hops; }
+    ub = q;
+    ut = p.t_begin + r;
+  };
+  auto film_prefetch = [&](int tl) {
+    int pb, pt;
+    split_tile(tl, pb, pt);
     for (int i = wt; i < 3 * kFilm / 4; i += 128) {
       const int slot = i / (kFilm / 4), fr = pt - 1 + slot;
       if (fr >= 0 && fr < T)
@@ -230,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     claimed = atomicAdd(p.tile_counter, 1);
   }
   wg_barrier(wg);
-  long long tile = tile_s[wg][0];
+  int tile = tile_s[wg][0];
   if (tile < n_tiles) film_prefetch(tile);
   int par = 0;
   for (;;) {
@@ -239,7 +249,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       tile_s[wg][par ^ 1] = claimed;                  // the next tile: published by the scan barrier below
       claimed = atomicAdd(p.tile_counter, 1);         // the one after
     }
-    const int b = (int)(tile / hops), t = p.t_begin + (int)(tile - (long long)b * hops);
+    int b, t;
+    split_tile(tile, b, t);
     // ---- f0 upsample and the cumsum of generators.py:59 (fp64 scan + per-hop carry)
     const int n = t * kHop + wt;
     const NwsLerp lc = nws_lerp_coords(n, T, inv_hop);
@@ -292,7 +303,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       if (lane == 0) film_k[wg][wwarp] = make_float2(ka, kd);
     }
     wg_barrier(wg);   // coefficient table visible to the whole warpgroup before the shaper loop reads it; film rows dead
-    const long long tile_next = tile_s[wg][par ^ 1];
+    const int tile_next = tile_s[wg][par ^ 1];
     if (tile_next < n_tiles) film_prefetch(tile_next);
     float mix_ka, mix_kd;   // this half-hop's constant part of the mixdown
     {
@@ -302,6 +313,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     }
 
     // ---- oscillator bank -> A operand stages -> tcgen05.mma
+    // Fast path, decided per warp and tile: no harmonic of any lane is masked (f0 * 104 < 8000 Hz everywhere —
+    // every control stream below 76.9 Hz, all of the timing scripts' inputs) — the stage loop is fully unrolled,
+    // so harmonic numbers are immediates and there is no per-stage classification.  Otherwise the general loop.
+    const bool tile_all_on =
+        __all_sync(0xffffffffu, NWS_MUL(f0u, (float)kHarmPad) < 0.5f * kSampleRate && !(f0u != f0u));
+    if (tile_all_on) {
+#pragma unroll
+      for (int st = 0; st < C::NST; ++st) {
+        const int buf = st & 1, k0 = st * C::KS;
+        const uint32_t prior = buf ? uses1 : uses0;
+        if (prior > 0 && ok) ok = nws_mbar_wait(&free_bar[wg][buf], (prior - 1) & 1);
+        const uint32_t col_hi = tmem_lane + C::kColA + buf * 2 * C::KS, col_lo = col_hi + C::KS;
+#pragma unroll
+        for (int kk = 0; kk < C::KS; kk += 8) {
+          if (k0 + kk < kHarmPad) {
+            float h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL((float)(k0 + kk + j + 1), phase), sm_shift[k0 + kk + j]));
+              h[j] = nws_tf32_hi(s);
+              l[j] = s - h[j];
+            }
+            tmem_st8(col_hi + kk, h);
+            tmem_st8(col_lo + kk, l);
+          }
+        }
+        tmem_wait_st();
+        nws_tc_fence_before();
+        fill_arrive(wg, buf);
+        if (buf) ++uses1; else ++uses0;
+      }
+    } else {
 #pragma unroll 1
     for (int st = 0; st < C::NST; ++st) {
       const int buf = st & 1, k0 = st * C::KS;
@@ -354,6 +397,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       fill_arrive(wg, buf);
       if (buf) ++uses1; else ++uses0;
     }
+    }
     // the noise-branch sample that is added to the mixdown at the very end: its latency hides behind the shaper loop
     const float noise_v = p.noise_in ? p.noise_in[(size_t)b * N + n] : 0.f;   // (aliases p.out: plain load)
     {  // accumulator complete when the last stage's commit lands (a commit covers all earlier MMAs)
@@ -391,7 +435,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
           // FastNEWT.shaping_fn (shaping.py:136-151): same index arithmetic as nws_lut_index — floor and clamp
           // done on the integer side (F2I.FLOOR saturates, NaN -> 0 with a NaN fract, as floorf/fmaxf/fminf give);
           // the table row holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
-          const float idx = nws_div_markstein(NWS_MUL(lut_size_f, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
+          // MODE 2 (size 4096 = 2^12): the multiply by the size is folded into the division's constants — scaling
+          // by a power of two commutes with every rounding of the Markstein sequence, so idx is bit-identical
+          const float idx = MODE == 2 ? nws_div_markstein(NWS_ADD(x, -lut_min), lut_span * (1.0f / 4096.0f), lut_rcp * 4096.0f)
+                                      : nws_div_markstein(NWS_MUL(lut_size_f, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
           const int fi = nws_min_relu(__float2int_rd(idx), lut_size - 1);   // clamp to [0, size-1]: one VIMNMX.RELU
           const float2 t2 = __ldg(lut_row + i * lut_size + (uint32_t)fi);
           y = fmaf(t2.y, NWS_ADD(idx, -(float)fi), t2.x);
@@ -446,6 +493,8 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
   }
   const long long tiles = (long long)B * (t_end - t_begin);
+  if (tiles >= (1ll << 31) - 4096 || t_end <= t_begin) { nws_set_error("nws_launch_audio_tc: bad tile count"); return NWS_ERR_INVALID; }
+  p.hops_magic = (uint32_t)((1ull << 32) / (uint64_t)(t_end - t_begin) > 0xffffffffull ? 0xffffffffull : (1ull << 32) / (uint64_t)(t_end - t_begin));
   const long long want = (tiles + kWgs - 1) / kWgs;
   const int cap = max_ctas > 0 && max_ctas < ctx->sm_count ? max_ctas : ctx->sm_count;   // SMs left to a concurrent encoder
   const int grid = (int)(want < cap ? want : cap);
