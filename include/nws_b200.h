@@ -209,6 +209,36 @@ int nws_selftest_umma(const float* A, const float* B, float* D, int K, int swap_
  * the SFU-based versions (quarter-turn reduction + sin/cos select; full-turn reduction, one MUFU) on x[0..n). */
 int nws_selftest_sin(const float* x, float* y_accurate, float* y_quarter, float* y_turn, long long n, void* stream);
 
+/* ---- stateful streaming: the same forward fed a few control frames at a time.
+ * The reference only times independent, stateless forwards per buffer size (scripts/time_buffer_sizes.py:
+ * 35-72); a real-time caller needs what crosses a buffer boundary carried over: the GRU state
+ * (neural_waveshaping.py:21,25), the running phase sum (generators.py:59), the neighbouring frames of the x128
+ * linear upsampling (neural_waveshaping.py:75, shaping.py:69) and of the noise overlap-add (generators.py:31-35),
+ * and the reverb's past input (shaping.py:161-173).  Contract: the concatenation of the audio returned by the
+ * pushes (+ the flush) equals the dry signal of ONE nws_forward over the concatenated frames, convolved
+ * causally with [0, ir] (the reference's circular wrap of the reverb tail has no streaming equivalent).
+ * Output lags input by one hop: hop h interpolates towards frame h+1. */
+typedef struct NwsStreamState* NwsStreamHandle;
+/* State for B parallel streams, at most max_frames (2..4096) control frames per push.  Owns its device memory. */
+int nws_stream_create(NwsHandle handle, int B, int max_frames, NwsStreamHandle* out_stream);
+int nws_stream_destroy(NwsStreamHandle stream_state);
+/* Start of an utterance: zero state.  u_phase (device, [101]) = the phase-shift draw of generators.py:55, fixed
+ * for the whole stream, or NULL -> Philox(seed, offset) — the same values nws_forward(seed, offset) would draw. */
+int nws_stream_reset(NwsStreamHandle stream_state, const float* u_phase, uint64_t seed, uint64_t offset, void* stream);
+/* The kernels run on a window of [<= 3 history frames | n_frames new frames]: first_frame = index of the
+ * window's first frame in the utterance, window_frames = its length.  For callers that inject the noise. */
+int nws_stream_window(NwsStreamHandle stream_state, int n_frames, long long* first_frame, int* window_frames);
+/* f0 [B,1,n_frames], control [B,ctrl_channels,n_frames] (device).  noise_window: NULL -> Philox draws indexed
+ * by absolute sample (same stream as nws_forward), or device [128*window_frames - 1] = the utterance's noise
+ * vector (generators.py:30) from sample 128*first_frame on.  flush != 0: these are the utterance's last frames
+ * (n_frames may be 0): the pending hop is rendered with the reference's end-of-signal clamping and the stream
+ * must be reset before the next push.  apply_reverb = 0 returns the dry signal.
+ * out [B, 128 * *n_out_frames] (device, room for 128*(n_frames+1) samples per row); *n_out_frames (host) =
+ * n_frames - 1 on the first push, n_frames afterwards, + 1 with flush.  The first push needs n_frames >= 2. */
+int nws_stream_push(NwsStreamHandle stream_state, const float* f0, const float* control, int ctrl_channels,
+                    int n_frames, const float* noise_window, int use_lut, int flush, int apply_reverb, float* out,
+                    int* n_out_frames, void* stream);
+
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 uint64_t nws_launch_count(int reset);

@@ -110,6 +110,13 @@ def load_library():
         L.nws_set_profiling.restype = c_int
         L.nws_get_stage_times.argtypes = [vp, POINTER(c_float), c_int]
         L.nws_get_stage_times.restype = c_int
+        L.nws_stream_create.argtypes = [vp, c_int, c_int, POINTER(vp)]
+        L.nws_stream_destroy.argtypes = [vp]
+        L.nws_stream_reset.argtypes = [vp, vp, c_uint64, c_uint64, vp]
+        L.nws_stream_window.argtypes = [vp, c_int, POINTER(ctypes.c_longlong), POINTER(c_int)]
+        L.nws_stream_push.argtypes = [vp, vp, vp, c_int, c_int, vp, c_int, c_int, c_int, vp, POINTER(c_int), vp]
+        for name in ("nws_stream_create", "nws_stream_destroy", "nws_stream_reset", "nws_stream_window", "nws_stream_push"):
+            getattr(L, name).restype = c_int
         L.nws_shaper_eval_scratch_bytes.restype = c_size_t
         L.nws_shaper_eval.argtypes = [POINTER(vp), vp, vp, c_int, vp, vp]
         for name in ("nws_create", "nws_destroy", "nws_load_weights", "nws_build_lut", "nws_set_lut", "nws_get_lut",
@@ -132,6 +139,7 @@ EXPORTED_SYMBOLS = [
     "nws_stage_control_embedding", "nws_stage_td_mlp", "nws_stage_audio", "nws_stage_lut_lookup", "nws_stage_noise", "nws_stage_reverb",
     "nws_reverb_workspace_bytes", "nws_shaper_eval_scratch_bytes", "nws_shaper_eval", "nws_launch_count",
     "nws_set_profiling", "nws_get_stage_times", "nws_selftest_umma", "nws_set_audio_impl", "nws_set_mlp_impl", "nws_stage_control_to_params", "nws_selftest_sin", "nws_set_pipeline",
+    "nws_stream_create", "nws_stream_destroy", "nws_stream_reset", "nws_stream_window", "nws_stream_push",
 ]
 STAGE_NAMES = ["rng", "phase_carry", "gru", "proj", "film_mlp", "noise_mlp", "noise_spectrum", "noise_filter",
                "audio_fused", "reverb"]

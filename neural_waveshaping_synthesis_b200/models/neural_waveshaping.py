@@ -185,6 +185,11 @@ class NeuralWaveshaping(nn.Module):
         return eng.forward_host(f0.contiguous(), control.contiguous(), out, phase_shift, noise,
                                 use_lut=isinstance(self.newt, FastNEWT))
 
+    def stream(self, batch_size: int = 1, max_frames: int = 32):
+        """Stateful streaming synthesis (extension): see streaming.SynthStream."""
+        from ..streaming import SynthStream
+        return SynthStream(self, batch_size, max_frames)
+
     # ------------------------------------------------------------------ Lightning-compatible loading
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):

@@ -292,6 +292,18 @@ def reverb_literal(ir: np.ndarray, x: np.ndarray) -> np.ndarray:
     return x + ylin[..., :N] + tail
 
 
+def reverb_causal(ir: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """The reverb as a causal (linear) convolution, float64: out[n] = x[n] + sum_j [0, ir][j] x[n-j].
+    This is what a stream can produce — Reverb.forward (shaping.py:161-173) additionally wraps the tail
+    ylin[n + L] back onto the start (reverb_literal), which needs the whole utterance.  Oracle of the
+    streaming extension (nws_stream_push)."""
+    ir_ = np.concatenate(([0.0], ir.astype(np.float64).ravel()))
+    N = x.shape[-1]
+    nfft = 1 << int(np.ceil(np.log2(N + ir_.shape[0])))
+    ylin = np.fft.irfft(np.fft.rfft(x.astype(np.float64), nfft) * np.fft.rfft(ir_, nfft), nfft)
+    return x + ylin[..., :N]
+
+
 # -------------------------------------------------------------------- full path
 def forward(w: Weights, f0: torch.Tensor, control: torch.Tensor, u_phase: torch.Tensor,
             noise: torch.Tensor, lut: Optional[torch.Tensor] = None, faithful_loop: bool = False,

@@ -464,3 +464,129 @@ def test_host_pipeline_matches_direct_forwards():
     assert pipe.d2h_bytes == sum(B * T * 128 * 4 for B, T in shapes)
     assert pipe.h2d_bytes == sum(B * T * 3 * 4 for B, T in shapes)
     assert list(HostPipeline(m, "cuda:0").run(iter([]))) == []
+
+
+# ------------------------------------------------------------------------------ streaming
+def _stream_expected(tag, fast, f0, control, u, noise):
+    """Oracle of the streaming extension: dry signal of ONE whole-utterance forward, then the causal reverb."""
+    w = load_weights(tag)
+    lut = oracle.build_lookup_table(w) if fast else None
+    _, parts = oracle.forward(w, f0, control, u, noise, lut=lut, return_parts=True)
+    dry = parts["dry"].numpy()
+    wet = oracle.reverb_causal(w["reverb.ir"].numpy(), dry)
+    return torch.from_numpy(dry), torch.from_numpy(wet).float()
+
+
+def _run_stream(m, f0, control, u, noise, chunks, reverb):
+    B, _, T = f0.shape
+    st = m.stream(batch_size=B, max_frames=max(chunks))
+    st.reset(phase_shift=u.reshape(-1))
+    outs, pos = [], 0
+    seq = list(chunks)
+    assert sum(seq) == T
+    for i, n in enumerate(seq):
+        first, tw = st.window(n)
+        assert first == max(pos - 3, 0) and tw == n + min(pos, 3)
+        nzw = torch.zeros(128 * tw - 1)
+        seg = noise[128 * first: 128 * first + 128 * tw - 1]      # the utterance's noise from the window's first sample
+        nzw[: seg.numel()] = seg
+        last = i == len(seq) - 1
+        y = st.push(f0[:, :, pos:pos + n].contiguous().cuda(), control[:, :, pos:pos + n].contiguous().cuda(),
+                    flush=last, noise_window=nzw, reverb=reverb)
+        exp_hops = n - (1 if i == 0 else 0) + (1 if last else 0)
+        assert y.shape == (B, 128 * exp_hops), (y.shape, exp_hops)
+        outs.append(y.cpu())
+        pos += n
+    return torch.cat(outs, dim=1)
+
+
+@pytest.mark.parametrize("tag,fast,chunks", [
+    ("randinit", True, [2, 2, 2, 2, 2]),          # 256-sample buffers, the smallest size of time_buffer_sizes.py
+    ("randinit", False, [4, 1, 3, 2]),             # ragged pushes, single-frame push
+    ("vn", True, [8, 8]),
+    ("vn", False, [5, 11]),
+])
+def test_stream_equals_whole_utterance(tag, fast, chunks):
+    """Chunked synthesis == the whole-utterance forward (dry), and == dry * causal reverb (wet)."""
+    m, w = _model(tag, fast)
+    T = sum(chunks)
+    if tag == "randinit":
+        g = torch.Generator().manual_seed(5)
+        f0, control = torch.rand(2, 1, T, generator=g), torch.rand(2, 2, T, generator=g)
+    else:
+        f0, control = oracle.realistic_inputs(T, w["data_mean"].numpy(), w["data_std"].numpy(), B=2)
+        f0[1] *= 0.5
+    u, noise = oracle.draw_rng(T, 11)
+    dry_ref, wet_ref = _stream_expected(tag, fast, f0, control, u, noise)
+    tol_max, tol_rms = _tols(tag)
+    dry = _run_stream(m, f0, control, u, noise, chunks, reverb=False)
+    e = err(dry, dry_ref)
+    assert e[0] <= tol_max and e[1] <= tol_rms, ("dry", e)
+    wet = _run_stream(m, f0, control, u, noise, chunks, reverb=True)
+    e = err(wet, wet_ref)
+    scale = max(1.0, float(wet_ref.abs().max()))
+    assert e[0] <= tol_max * scale and e[1] <= tol_rms * scale, ("wet", e)
+
+
+def test_stream_long_reverb_history():
+    """More than 32000 samples through the stream: the reverb history buffer wraps several times."""
+    m, w = _model("vn", True)
+    T, n = 320, 32                                   # 40960 samples in 10 pushes
+    f0, control = oracle.realistic_inputs(T, w["data_mean"].numpy(), w["data_std"].numpy(), B=1)
+    u, noise = oracle.draw_rng(T, 3)
+    _, wet_ref = _stream_expected("vn", True, f0, control, u, noise)
+    wet = _run_stream(m, f0, control, u, noise, [n] * (T // n), reverb=True)
+    e = err(wet, wet_ref)
+    scale = max(1.0, float(wet_ref.abs().max()))
+    assert e[0] <= TOL_CKPT_MAX * scale and e[1] <= TOL_CKPT_RMS * scale, e
+
+
+def test_stream_default_rng_matches_forward_draws():
+    """Without injected draws the stream uses the Philox values a whole-utterance forward with the same
+    (seed, offset) would: chunked dry output == whole-forward dry output of the library itself."""
+    import ctypes
+    from neural_waveshaping_synthesis_b200 import _lib
+    m, w = _model("randinit", True)
+    T = 12
+    g = torch.Generator().manual_seed(9)
+    f0, control = torch.rand(1, 1, T, generator=g).cuda(), torch.rand(1, 2, T, generator=g).cuda()
+    st = m.stream(batch_size=1, max_frames=4)
+    torch.manual_seed(123)
+    st.reset()
+    seed, off = st._seed, st._offset
+    outs = [st.push(f0[:, :, i:i + 4].contiguous(), control[:, :, i:i + 4].contiguous(), flush=(i == 8), reverb=False)
+            for i in range(0, T, 4)]
+    dry_stream = torch.cat(outs, dim=1)
+    # whole utterance, same draws: film/bands -> stage kernels would need the draws; use nws_forward's dry via a
+    # zero reverb IR instead (the reverb adds nothing when ir == 0)
+    m2, _ = _model("randinit", True)
+    with torch.no_grad():
+        m2.reverb.ir.zero_()
+    eng = m2._engine_for(f0)
+    out = torch.empty(1, 128 * T, device="cuda")
+    ws = eng.workspace_for(1, T)
+    lib = eng.lib
+    _lib.check(lib.nws_forward(eng.handle, ctypes.c_void_p(f0.data_ptr()), ctypes.c_void_p(control.data_ptr()), 2,
+                               ctypes.c_void_p(0), ctypes.c_void_p(0), seed, off, ctypes.c_void_p(out.data_ptr()), 1, T, 1,
+                               ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert err(dry_stream, out)[0] <= 2e-6
+
+
+def test_stream_errors():
+    m, _ = _model("randinit", False)
+    st = m.stream(batch_size=1, max_frames=4)
+    from neural_waveshaping_synthesis_b200._lib import NwsError
+    f0, c = torch.rand(1, 1, 4).cuda(), torch.rand(1, 2, 4).cuda()
+    with pytest.raises(NwsError):          # never reset
+        st.push(f0, c)
+    st.reset()
+    with pytest.raises(NwsError):          # first push needs two frames
+        st.push(f0[:, :, :1].contiguous(), c[:, :, :1].contiguous())
+    with pytest.raises(NwsError):          # more than max_frames
+        st.push(torch.rand(1, 1, 5).cuda(), torch.rand(1, 2, 5).cuda())
+    y = st.push(f0, c, flush=True)
+    assert y.shape == (1, 128 * 4)
+    with pytest.raises(NwsError):          # flushed
+        st.push(f0, c)
