@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
           // the table row holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
           // MODE 2 (size 4096 = 2^12): the multiply by the size is folded into the division's constants — scaling
           // by a power of two commutes with every rounding of the Markstein sequence, so idx is bit-identical
-          const float idx = MODE == 2 ? nws_div_markstein(NWS_ADD(x, -lut_min), lut_span * (1.0f / 4096.0f), lut_rcp * 4096.0f)
+          const float idx = MODE == 2 ? nws_lut_idx_pow2(x, lut_min, lut_span * (1.0f / 4096.0f), lut_rcp * 4096.0f)
                                       : nws_div_markstein(NWS_MUL(lut_size_f, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
           const int fi = nws_min_relu(__float2int_rd(idx), lut_size - 1);   // clamp to [0, size-1]: one VIMNMX.RELU
           const float2 t2 = __ldg(lut_row + i * lut_size + (uint32_t)fi);

@@ -153,6 +153,15 @@ NWS_HD float nws_div_markstein(float a, float d, float d_rcp) {
   return NWS_FMA(rem, d_rcp, q0);
 }
 
+// The un-floored index of nws_lut_index for a POWER-OF-TWO table size without the multiply by the size:
+// with s = x - min, idx = RN(size*s / span).  Scaling by 2^k commutes with every rounding of the Markstein
+// sequence (no overflow / underflow in range), so dividing s by span/size with the reciprocal size/span * ... gives
+// the bit-identical result: q0 = RN(s * (R*size)) = size*RN(s*R)... (tests/test_math_cpu.py checks every float).
+// `span_over_size` = span / size and `rcp_times_size` = RN(1/span) * size, both exact scalings.
+NWS_HD float nws_lut_idx_pow2(float x, float table_min, float span_over_size, float rcp_times_size) {
+  return nws_div_markstein(NWS_ADD(x, -table_min), span_over_size, rcp_times_size);
+}
+
 NWS_HD NwsLutIdx nws_lut_index(float x, int table_size, float table_min, float span, float span_rcp) {
   const float a = NWS_MUL((float)table_size, NWS_ADD(x, -table_min));
   const float idx = nws_div_markstein(a, span, span_rcp);

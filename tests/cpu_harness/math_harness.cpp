@@ -28,6 +28,24 @@ long h_div_check(float d, float lo_limit, float limit, long stride) {
   return bad;
 }
 
+// nws_lut_idx_pow2 against the index arithmetic of nws_lut_index (multiply by the size, then divide by the span)
+// for every finite float |x| <= limit (stepping `stride` bit patterns); returns the number of mismatches.
+long h_idx_pow2_check(int size, float tmin, float tmax, float limit, long stride) {
+  const float span = tmax - tmin, rcp = 1.0f / span;
+  const float span_s = span / (float)size, rcp_s = rcp * (float)size;
+  long bad = 0;
+  for (uint64_t bits = 0; bits < (1ull << 32); bits += (uint64_t)stride) {
+    uint32_t b = (uint32_t)bits;
+    float x;
+    memcpy(&x, &b, 4);
+    if (!(x == x) || x > limit || x < -limit) continue;
+    const float ref = nws_div_markstein(NWS_MUL((float)size, NWS_ADD(x, -tmin)), span, rcp);
+    const float got = nws_lut_idx_pow2(x, tmin, span_s, rcp_s);
+    if (memcmp(&ref, &got, 4) != 0 && !(ref == 0.0f && got == 0.0f)) ++bad;
+  }
+  return bad;
+}
+
 void h_upsample(const float* x, int T, int hop, float* y) {
   const float inv = (float)T / (float)(T * hop);
   for (int n = 0; n < T * hop; ++n) {

@@ -125,6 +125,15 @@ def test_lut_index_bit_exact(lib):
     assert np.array_equal(out, ref)
 
 
+def test_lut_index_pow2_fold_is_bit_identical(lib):
+    """The fused kernel's index for the default 4096-entry table (no multiply by the size) == nws_lut_index's."""
+    lib.h_idx_pow2_check.restype = ctypes.c_long
+    lib.h_idx_pow2_check.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_long]
+    assert lib.h_idx_pow2_check(4096, -3.0, 3.0, 1.0e4, 3) == 0          # every third float up to |x| = 1e4
+    assert lib.h_idx_pow2_check(4096, -1.0, 2.5, 100.0, 11) == 0
+    assert lib.h_idx_pow2_check(1024, -3.0, 3.0, 100.0, 11) == 0
+
+
 def test_philox_known_answer_and_uniformity(lib):
     raw = np.empty(4, np.uint32)
     # Random123 known-answer vector: counter = 0, key = 0
