@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) nws_noise_spectrum_kernel(const float* __
     buf_a[n] = make_float2(v[0], v[1]);
   }
   __syncthreads();
-  const float2* z = nws_fft_smem<false, false>(buf_a, buf_b, tw_s, 1, 8, 1, tid, 128);
+  const float2* z = nws_fft_smem<false, false>(buf_a, buf_b, tw_s, 1, 8, 0, tid, 128);
   for (int k = tid; k <= 128; k += 128) {
     const float2 zk = z[k], zc = z[(256 - k) & 255];
     // Xa = (Z[k] + conj(Z[N-k])) / 2 ; Xb = (Z[k] - conj(Z[N-k])) / (2i)
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) nws_noise_filter_kernel(const float* __re
     }
     __syncthreads();
     // both FFTs advance in lock-step (the helper's barriers are CTA-wide)
-    const float2* z = nws_fft_smem<true, false>(&buf_a[0][0], &buf_b[0][0], tw_s, 1, 8, 2, tid, 256);
+    const float2* z = nws_fft_smem<true, false>(&buf_a[0][0], &buf_b[0][0], tw_s, 1, 8, 1, tid, 256);
     for (int n = j; n < 256; n += 128) {
       const float2 v = z[g * 256 + n];
       y_s[2 * pair][n] = v.x * (1.0f / 256.0f);

@@ -29,8 +29,9 @@ __global__ void __launch_bounds__(256) nws_reverb_cols_fwd_kernel(const float* _
                                                                   float2* __restrict__ work,
                                                                   const float2* __restrict__ tw_big,
                                                                   const float2* __restrict__ tw_master, int n1,
-                                                                  int log_n1, int W) {
+                                                                  int log_n1, int log_w) {
   extern __shared__ __align__(16) float2 smem2[];
+  const int W = 1 << log_w;   // columns per CTA (a power of two: index arithmetic is shifts and masks)
   float2* a = smem2;
   float2* bb = smem2 + n1 * W;
   float2* tw_s = smem2 + 2 * n1 * W;
@@ -41,16 +42,16 @@ __global__ void __launch_bounds__(256) nws_reverb_cols_fwd_kernel(const float* _
   const float* xb = 2 * pair + 1 < B ? x + (size_t)(2 * pair + 1) * N : nullptr;
 #pragma unroll 4
   for (int i = tid; i < n1 * W; i += 256) {
-    const int r = i / W, c = i - r * W;
+    const int r = i >> log_w, c = i & (W - 1);
     const long long n = (long long)r * 256 + c0 + c;
     a[i] = n < N ? make_float2(__ldg(xa + n), xb ? __ldg(xb + n) : 0.f) : make_float2(0.f, 0.f);
   }
   __syncthreads();
-  const float2* z = nws_fft_smem<false, true>(a, bb, tw_s, 1, log_n1, W, tid, 256);
+  const float2* z = nws_fft_smem<false, true>(a, bb, tw_s, 1, log_n1, log_w, tid, 256);
   float2* dst = work + (size_t)pair * L;
 #pragma unroll 4
   for (int i = tid; i < n1 * W; i += 256) {
-    const int k1 = i / W, c = i - k1 * W;
+    const int k1 = i >> log_w, c = i & (W - 1);
     const size_t idx = (size_t)k1 * 256 + c0 + c;
     dst[idx] = nws_cmul(z[i], __ldg(tw_big + idx));
   }
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) nws_reverb_rows_kernel(float2* __restrict
   buf_a[g][j] = w[j];
   buf_a[g][j + 128] = w[j + 128];
   __syncthreads();
-  float2* z = nws_fft_smem<false, false>(&buf_a[0][0], &buf_b[0][0], tw_s, 1, 8, 2, tid, 256);
+  float2* z = nws_fft_smem<false, false>(&buf_a[0][0], &buf_b[0][0], tw_s, 1, 8, 1, tid, 256);
   if (mode == 1) {
     w[j] = z[g * 256 + j];
     w[j + 128] = z[g * 256 + j + 128];
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) nws_reverb_rows_kernel(float2* __restrict
   z[g * 256 + j] = nws_cmul(z[g * 256 + j], ir_spec[row + j]);
   z[g * 256 + j + 128] = nws_cmul(z[g * 256 + j + 128], ir_spec[row + j + 128]);
   __syncthreads();
-  const float2* y = nws_fft_smem<true, false>(z, other, tw_s, 1, 8, 2, tid, 256);
+  const float2* y = nws_fft_smem<true, false>(z, other, tw_s, 1, 8, 1, tid, 256);
   w[j] = y[g * 256 + j];
   w[j + 128] = y[g * 256 + j + 128];
 }
@@ -93,9 +94,10 @@ template <bool FUSE_FOLD>
 __global__ void __launch_bounds__(256) nws_reverb_cols_inv_kernel(float2* __restrict__ work,
                                                                   const float2* __restrict__ tw_big,
                                                                   const float2* __restrict__ tw_master, int n1,
-                                                                  int log_n1, int W, const float* __restrict__ x,
+                                                                  int log_n1, int log_w, const float* __restrict__ x,
                                                                   float* __restrict__ out, int B, int N, int Lc) {
   extern __shared__ __align__(16) float2 smem2[];
+  const int W = 1 << log_w;   // columns per CTA (a power of two: index arithmetic is shifts and masks)
   float2* a = smem2;
   float2* bb = smem2 + n1 * W;
   float2* tw_s = smem2 + 2 * n1 * W;
@@ -105,14 +107,14 @@ __global__ void __launch_bounds__(256) nws_reverb_cols_inv_kernel(float2* __rest
   for (int i = tid; i < n1 / 2; i += 256) tw_s[i] = tw_master[i * (kTwMaster / n1)];
 #pragma unroll 4
   for (int i = tid; i < n1 * W; i += 256) {
-    const int k1 = i / W, c = i - k1 * W;
+    const int k1 = i >> log_w, c = i & (W - 1);
     const size_t idx = (size_t)k1 * 256 + c0 + c;
     float2 t = __ldg(tw_big + idx);
     t.y = -t.y;
     a[i] = nws_cmul(wk[idx], t);
   }
   __syncthreads();
-  const float2* z = nws_fft_smem<true, true>(a, bb, tw_s, 1, log_n1, W, tid, 256);
+  const float2* z = nws_fft_smem<true, true>(a, bb, tw_s, 1, log_n1, log_w, tid, 256);
   const float scale = 1.0f / (float)L;
   if (FUSE_FOLD) {
     // out[b][n] = x[b][n] + y[n] + y[n + Lc], y = linear convolution (zero beyond N + 31998)
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(256) nws_reverb_cols_inv_kernel(float2* __rest
     const long long ylen = (long long)N + kReverbIr - 1;
     const int b0 = 2 * pair, b1 = 2 * pair + 1;
     for (int i = tid; i < rows * W; i += 256) {
-      const int r = i / W, c = i - r * W;
+      const int r = i >> log_w, c = i & (W - 1);
       const long long n = (long long)r * 256 + c0 + c;
       if (n >= N) continue;
       float2 v = z[i];
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(256) nws_reverb_cols_inv_kernel(float2* __rest
     }
   } else {
     for (int i = tid; i < n1 * W; i += 256) {
-      const int r = i / W, c = i - r * W;
+      const int r = i >> log_w, c = i & (W - 1);
       const float2 v = z[i];
       wk[(size_t)r * 256 + c0 + c] = make_float2(v.x * scale, v.y * scale);
     }
@@ -161,6 +163,8 @@ __global__ void __launch_bounds__(256) nws_reverb_fold_kernel(const float* __res
 
 // ---------------------------------------------------------------------------------------------- plans
 static size_t cols_smem_bytes(int n1, int W) { return ((size_t)2 * n1 * W + n1 / 2) * sizeof(float2); }
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 static int pick_cols(int n1) {
   int W = 4096 / n1;  // 64 KB of ping-pong buffers: three CTAs per SM keep more loads in flight
@@ -200,7 +204,7 @@ static int launch_cols_fwd(NwsContext* ctx, NwsReverbPlan* pl, const float* x, i
   const int W = pl->cols_per_cta;
   dim3 grid(256 / W, (B + 1) / 2);
   nws_reverb_cols_fwd_kernel<<<grid, 256, cols_smem_bytes(pl->n1, W), s>>>(x, B, N, work, pl->tw_big, ctx->tw_master,
-                                                                          pl->n1, pl->log_n1, W);
+                                                                          pl->n1, pl->log_n1, ilog2(W));
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }
@@ -264,11 +268,11 @@ int nws_launch_reverb(NwsContext* ctx, const float* x, float* out, float2* work,
   if (Lc % 256 == 0) {
     // (x + y*scale: the scale is applied to the sum y[n] + y[n+Lc] — same value up to one rounding)
     nws_reverb_cols_inv_kernel<true><<<dim3(256 / W, n_pairs), 256, cols_smem_bytes(pl->n1, W), s>>>(
-        work, pl->tw_big, ctx->tw_master, pl->n1, pl->log_n1, W, x, out, B, N, Lc);
+        work, pl->tw_big, ctx->tw_master, pl->n1, pl->log_n1, ilog2(W), x, out, B, N, Lc);
     NWS_LAUNCH_CHECK();
   } else {
     nws_reverb_cols_inv_kernel<false><<<dim3(256 / W, n_pairs), 256, cols_smem_bytes(pl->n1, W), s>>>(
-        work, pl->tw_big, ctx->tw_master, pl->n1, pl->log_n1, W, x, out, B, N, Lc);
+        work, pl->tw_big, ctx->tw_master, pl->n1, pl->log_n1, ilog2(W), x, out, B, N, Lc);
     NWS_LAUNCH_CHECK();
     nws_reverb_fold_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, work, out, B, N, (size_t)L, Lc);
     NWS_LAUNCH_CHECK();

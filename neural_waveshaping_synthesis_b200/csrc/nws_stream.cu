@@ -166,7 +166,7 @@ extern "C" int nws_stream_create(NwsHandle ctx, int B, int max_frames, NwsStream
   if (!ctx->weights_loaded) { nws_set_error("nws_stream_create: weights not loaded"); return NWS_ERR_STATE; }
   NwsStreamState* st = new NwsStreamState();
   st->ctx = ctx; st->B = B; st->max_frames = max_frames; st->Tw_max = max_frames + kHist;
-  const size_t Nx_max = (size_t)kReverbIr + (size_t)kHop * max_frames;
+  const size_t Nx_max = (size_t)kReverbIr + (size_t)kHop * (max_frames + 1);   // a flushing push emits max_frames + 1 hops
   const int L = nws_reverb_fft_len((int)Nx_max);
   if (!L) { delete st; nws_set_error("nws_stream_create: max_frames too large for the reverb plan"); return NWS_ERR_UNSUPPORTED; }
   st->ws_bytes = nws_carve_workspace(nullptr, B, st->Tw_max, 256).total;

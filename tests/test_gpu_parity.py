@@ -525,7 +525,11 @@ def test_stream_equals_whole_utterance(tag, fast, chunks):
     wet = _run_stream(m, f0, control, u, noise, chunks, reverb=True)
     e = err(wet, wet_ref)
     scale = max(1.0, float(wet_ref.abs().max()))
-    assert e[0] <= tol_max * scale and e[1] <= tol_rms * scale, ("wet", e)
+    d = (wet - wet_ref).abs()
+    where = torch.nonzero(d > tol_max * scale)
+    assert e[0] <= tol_max * scale and e[1] <= tol_rms * scale, (
+        "wet", e, "bad samples", where.shape[0], "first", where[0].tolist() if where.numel() else None,
+        "last", where[-1].tolist() if where.numel() else None)
 
 
 def test_stream_long_reverb_history():
