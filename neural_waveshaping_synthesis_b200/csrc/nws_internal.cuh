@@ -80,7 +80,9 @@ inline NwsPackedLayout nws_packed_layout() {
 
 // ------------------------------------------------------------------ reverb FFT plan
 struct NwsReverbPlan {
-  int n1 = 0, log_n1 = 0;      // column FFT length; L = n1 * 256
+  int n1 = 0, log_n1 = 0;      // column FFT length; L = n1 * 256 (log_n1: power-of-two lengths only)
+  bool mixed = false;          // n1 = 125 or 250: mixed-radix column transforms (nws_fft_mixed.cuh)
+  float2* tw_cols = nullptr;   // [n1]  exp(-2*pi*i*m/n1) (mixed plans)
   int cols_per_cta = 0;        // W
   float2* tw_big = nullptr;    // [L]   exp(-2*pi*i*n2*k1/L) at index k1*256+n2
   float2* ir_spec = nullptr;   // [L]   spectrum of [0, ir] in the four-step layout
@@ -147,6 +149,7 @@ struct NwsWorkspace {
 
 NwsWorkspace nws_carve_workspace(void* base, int B, int T, int fft_len);
 int nws_reverb_fft_len(int N);  // L = n1*256 >= N + kReverbIr - 1, n1 a power of two >= 128; 0 if unsupported
+int nws_reverb_exact_len(int N); // max(N, kReverbIr) when the circular convolution can run at exactly that length, else 0
 
 // ------------------------------------------------------------------ error / launch bookkeeping
 void nws_set_error(const char* fmt, ...);

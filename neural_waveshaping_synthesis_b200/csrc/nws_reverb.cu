@@ -10,16 +10,31 @@
 //   R3  conj twiddle + inverse column FFTs, 1/L                   -> work (time domain, complex pair)
 //   R4  fold the circular wrap and add the dry signal             -> out
 // The IR spectrum (same four-step layout) and the big twiddle table are cached per transform length.
+//
+// Exact-length plans.  When Lc itself is n1 * 256 with n1 = 250 (N = 64000: the 4 s utterances of every
+// benchmark config), n1 = 125 (Lc = 32000: everything up to 2 s) or a power of two (N = 32768), the circular
+// convolution runs at exactly Lc points — mixed-radix column transforms (nws_fft_mixed.cuh) — and there is
+// no wrap to fold: half the points of the padded transform (64000 instead of 131072).
 #include <math.h>
 #include <stdlib.h>
 
 #include "nws_fft.cuh"
+#include "nws_fft_mixed.cuh"
 #include "nws_internal.cuh"
 
 int nws_reverb_fft_len(int N) {
   const long long need = (long long)N + kReverbIr - 1;
   for (int n1 = 128; n1 <= kTwMaster; n1 <<= 1)
     if ((long long)n1 * 256 >= need) return n1 * 256;
+  return 0;
+}
+
+int nws_reverb_exact_len(int N) {
+  const int Lc = N > kReverbIr ? N : kReverbIr;
+  if (Lc % 256) return 0;
+  const int n1 = Lc / 256;
+  if (n1 == 125 || n1 == 250) return Lc;
+  if (n1 >= 128 && n1 <= kTwMaster && (n1 & (n1 - 1)) == 0) return Lc;
   return 0;
 }
 
@@ -57,24 +72,100 @@ __global__ void __launch_bounds__(256) nws_reverb_cols_fwd_kernel(const float* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- R1 / R3, mixed radix
+// Exact-length plans (n1 = N1 in {125, 250}): grid (256 / W, n_pairs); dynamic smem (2 * N1 * W + N1) float2.
+template <int N1>
+__global__ void __launch_bounds__(256) nws_reverb_cols_fwd_mixed_kernel(const float* __restrict__ x, int B, int N,
+                                                                        float2* __restrict__ work,
+                                                                        const float2* __restrict__ tw_big,
+                                                                        const float2* __restrict__ tw_cols, int log_w) {
+  extern __shared__ __align__(16) float2 smem2[];
+  const int W = 1 << log_w;
+  float2* a = smem2;
+  float2* bb = smem2 + N1 * W;
+  float2* tw_s = smem2 + 2 * N1 * W;
+  const int tid = threadIdx.x, pair = blockIdx.y, c0 = blockIdx.x * W;
+  for (int i = tid; i < N1; i += 256) tw_s[i] = tw_cols[i];
+  const float* xa = x + (size_t)(2 * pair) * N;
+  const float* xb = 2 * pair + 1 < B ? x + (size_t)(2 * pair + 1) * N : nullptr;
+#pragma unroll 4
+  for (int i = tid; i < N1 * W; i += 256) {
+    const int r = i >> log_w, c = i & (W - 1);
+    const int n = r * 256 + c0 + c;
+    a[i] = n < N ? make_float2(__ldg(xa + n), xb ? __ldg(xb + n) : 0.f) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const float2* z = nws_fft_mixed<N1, false>(a, bb, tw_s, log_w, tid, 256);
+  float2* dst = work + (size_t)pair * (N1 * 256);
+#pragma unroll 4
+  for (int i = tid; i < N1 * W; i += 256) {
+    const int k1 = i >> log_w, c = i & (W - 1);
+    const int idx = k1 * 256 + c0 + c;
+    dst[idx] = nws_cmul(z[i], __ldg(tw_big + idx));
+  }
+}
+
+// conj twiddle + inverse column transforms, 1/L, dry add: out[b][n] = x[b][n] + y[n] (the transform length IS the
+// circular length: nothing to fold)
+template <int N1>
+__global__ void __launch_bounds__(256) nws_reverb_cols_inv_mixed_kernel(const float2* __restrict__ work,
+                                                                        const float2* __restrict__ tw_big,
+                                                                        const float2* __restrict__ tw_cols, int log_w,
+                                                                        const float* __restrict__ x,
+                                                                        float* __restrict__ out, int B, int N) {
+  extern __shared__ __align__(16) float2 smem2[];
+  const int W = 1 << log_w;
+  float2* a = smem2;
+  float2* bb = smem2 + N1 * W;
+  float2* tw_s = smem2 + 2 * N1 * W;
+  const int tid = threadIdx.x, c0 = blockIdx.x * W, pair = blockIdx.y;
+  const float2* wk = work + (size_t)pair * (N1 * 256);
+  for (int i = tid; i < N1; i += 256) tw_s[i] = tw_cols[i];
+#pragma unroll 4
+  for (int i = tid; i < N1 * W; i += 256) {
+    const int k1 = i >> log_w, c = i & (W - 1);
+    const int idx = k1 * 256 + c0 + c;
+    float2 t = __ldg(tw_big + idx);
+    t.y = -t.y;
+    a[i] = nws_cmul(wk[idx], t);
+  }
+  __syncthreads();
+  const float2* z = nws_fft_mixed<N1, true>(a, bb, tw_s, log_w, tid, 256);
+  const float scale = 1.0f / (float)(N1 * 256);
+  const int rows = (N + 255) / 256;   // <= N1
+  const int b0 = 2 * pair, b1 = 2 * pair + 1;
+  for (int i = tid; i < rows * W; i += 256) {
+    const int r = i >> log_w, c = i & (W - 1);
+    const int n = r * 256 + c0 + c;
+    if (n >= N) continue;
+    const float2 v = z[i];
+    out[(size_t)b0 * N + n] = x[(size_t)b0 * N + n] + v.x * scale;
+    if (b1 < B) out[(size_t)b1 * N + n] = x[(size_t)b1 * N + n] + v.y * scale;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- R2
-// grid (n1 / 2, n_pairs), 256 threads = two rows.  mode 0: fwd FFT, * ir_spec, inverse FFT.
-// mode 1 (plan building): fwd FFT only (the result IS the IR spectrum).
+// grid ((n1 + 1) / 2, n_pairs), 256 threads = two rows (the second one idles in the last CTA of an odd n1).
+// mode 0: fwd FFT, * ir_spec, inverse FFT.  mode 1 (plan building): fwd FFT only (the result IS the IR spectrum).
 __global__ void __launch_bounds__(256) nws_reverb_rows_kernel(float2* __restrict__ work, const float2* __restrict__ ir_spec,
                                                               const float2* __restrict__ tw_master, int n1, int mode) {
   __shared__ float2 buf_a[2][256], buf_b[2][256], tw_s[128];
   const int tid = threadIdx.x, g = tid >> 7, j = tid & 127;
   const size_t L = (size_t)n1 * 256;
-  const size_t row = (size_t)(2 * blockIdx.x + g) * 256;
+  const bool live = 2 * (int)blockIdx.x + g < n1;
+  const size_t row = live ? (size_t)(2 * blockIdx.x + g) * 256 : 0;
   float2* w = work + (size_t)blockIdx.y * L + row;
   for (int i = tid; i < 128; i += 256) tw_s[i] = tw_master[i * (kTwMaster / 256)];
-  buf_a[g][j] = w[j];
-  buf_a[g][j + 128] = w[j + 128];
+  buf_a[g][j] = live ? w[j] : make_float2(0.f, 0.f);
+  buf_a[g][j + 128] = live ? w[j + 128] : make_float2(0.f, 0.f);
   __syncthreads();
   float2* z = nws_fft_smem<false, false>(&buf_a[0][0], &buf_b[0][0], tw_s, 1, 8, 1, tid, 256);
   if (mode == 1) {
-    w[j] = z[g * 256 + j];
-    w[j + 128] = z[g * 256 + j + 128];
+    if (live) {
+      w[j] = z[g * 256 + j];
+      w[j + 128] = z[g * 256 + j + 128];
+    }
     return;
   }
   float2* other = z == &buf_a[0][0] ? &buf_b[0][0] : &buf_a[0][0];
@@ -82,8 +173,10 @@ __global__ void __launch_bounds__(256) nws_reverb_rows_kernel(float2* __restrict
   z[g * 256 + j + 128] = nws_cmul(z[g * 256 + j + 128], ir_spec[row + j + 128]);
   __syncthreads();
   const float2* y = nws_fft_smem<true, false>(z, other, tw_s, 1, 8, 1, tid, 256);
-  w[j] = y[g * 256 + j];
-  w[j + 128] = y[g * 256 + j + 128];
+  if (live) {
+    w[j] = y[g * 256 + j];
+    w[j + 128] = y[g * 256 + j + 128];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- R3
@@ -163,6 +256,7 @@ __global__ void __launch_bounds__(256) nws_reverb_fold_kernel(const float* __res
 
 // ---------------------------------------------------------------------------------------------- plans
 static size_t cols_smem_bytes(int n1, int W) { return ((size_t)2 * n1 * W + n1 / 2) * sizeof(float2); }
+static size_t cols_mixed_smem_bytes(int n1, int W) { return ((size_t)2 * n1 * W + n1) * sizeof(float2); }
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -196,6 +290,7 @@ void nws_reverb_free_plans(NwsContext* ctx) {
   for (int i = 0; i < ctx->n_plans; ++i) {
     cudaFree(ctx->plans[i].tw_big);
     cudaFree(ctx->plans[i].ir_spec);
+    cudaFree(ctx->plans[i].tw_cols);
   }
   ctx->n_plans = 0;
 }
@@ -203,6 +298,13 @@ void nws_reverb_free_plans(NwsContext* ctx) {
 static int launch_cols_fwd(NwsContext* ctx, NwsReverbPlan* pl, const float* x, int B, int N, float2* work, cudaStream_t s) {
   const int W = pl->cols_per_cta;
   dim3 grid(256 / W, (B + 1) / 2);
+  if (pl->mixed) {
+    const size_t smem = cols_mixed_smem_bytes(pl->n1, W);
+    if (pl->n1 == 125) nws_reverb_cols_fwd_mixed_kernel<125><<<grid, 256, smem, s>>>(x, B, N, work, pl->tw_big, pl->tw_cols, ilog2(W));
+    else nws_reverb_cols_fwd_mixed_kernel<250><<<grid, 256, smem, s>>>(x, B, N, work, pl->tw_big, pl->tw_cols, ilog2(W));
+    NWS_LAUNCH_CHECK();
+    return NWS_OK;
+  }
   nws_reverb_cols_fwd_kernel<<<grid, 256, cols_smem_bytes(pl->n1, W), s>>>(x, B, N, work, pl->tw_big, ctx->tw_master,
                                                                           pl->n1, pl->log_n1, ilog2(W));
   NWS_LAUNCH_CHECK();
@@ -219,9 +321,23 @@ int nws_reverb_get_plan(NwsContext* ctx, int fft_len, cudaStream_t s, NwsReverbP
     pl = &ctx->plans[ctx->n_plans];
     *pl = NwsReverbPlan();
     pl->n1 = n1;
+    pl->mixed = n1 == 125 || n1 == 250;
     for (pl->log_n1 = 0; (1 << pl->log_n1) < n1; ++pl->log_n1) {}
-    pl->cols_per_cta = pick_cols(n1);
+    pl->cols_per_cta = pl->mixed ? 16 : pick_cols(n1);   // mixed: 2 x 31.25 KB (n1 = 250) of ping-pong buffers per CTA
     const size_t L = (size_t)fft_len;
+    if (pl->mixed) {
+      float2 hc[250];
+      for (int m = 0; m < n1; ++m) {
+        const double a = -2.0 * M_PI * (double)m / (double)n1;
+        hc[m] = make_float2((float)cos(a), (float)sin(a));
+      }
+      NWS_CUDA_OK(cudaMalloc(&pl->tw_cols, n1 * sizeof(float2)));
+      NWS_CUDA_OK(cudaMemcpy(pl->tw_cols, hc, n1 * sizeof(float2), cudaMemcpyHostToDevice));
+      NWS_CUDA_OK(cudaFuncSetAttribute(nws_reverb_cols_fwd_mixed_kernel<125>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      NWS_CUDA_OK(cudaFuncSetAttribute(nws_reverb_cols_fwd_mixed_kernel<250>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      NWS_CUDA_OK(cudaFuncSetAttribute(nws_reverb_cols_inv_mixed_kernel<125>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      NWS_CUDA_OK(cudaFuncSetAttribute(nws_reverb_cols_inv_mixed_kernel<250>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    }
     NWS_CUDA_OK(cudaMalloc(&pl->tw_big, L * sizeof(float2)));
     NWS_CUDA_OK(cudaMalloc(&pl->ir_spec, L * sizeof(float2)));
     float2* h = (float2*)malloc(L * sizeof(float2));
@@ -245,7 +361,7 @@ int nws_reverb_get_plan(NwsContext* ctx, int fft_len, cudaStream_t s, NwsReverbP
     // spectrum of [0, ir] (shaping.py:162) in the four-step layout: R1 then the forward half of R2
     int rc = launch_cols_fwd(ctx, pl, ctx->packed + ctx->lay.ir, 1, kReverbIr, pl->ir_spec, s);
     if (rc) return rc;
-    nws_reverb_rows_kernel<<<dim3(n1 / 2, 1), 256, 0, s>>>(pl->ir_spec, nullptr, ctx->tw_master, n1, 1);
+    nws_reverb_rows_kernel<<<dim3((n1 + 1) / 2, 1), 256, 0, s>>>(pl->ir_spec, nullptr, ctx->tw_master, n1, 1);
     NWS_LAUNCH_CHECK();
     pl->ir_valid = true;
   }
@@ -254,7 +370,10 @@ int nws_reverb_get_plan(NwsContext* ctx, int fft_len, cudaStream_t s, NwsReverbP
 }
 
 int nws_launch_reverb(NwsContext* ctx, const float* x, float* out, float2* work, int B, int N, cudaStream_t s) {
-  const int L = nws_reverb_fft_len(N);
+  // exact: the transform length is the circular length itself (never longer than the padded plan the workspace is
+  // sized for)
+  const int exact = nws_reverb_exact_len(N);
+  const int L = exact ? exact : nws_reverb_fft_len(N);
   if (!L) { nws_set_error("reverb: N = %d too long for the FFT plan (max %d samples)", N, kTwMaster * 256 - kReverbIr); return NWS_ERR_UNSUPPORTED; }
   NwsReverbPlan* pl = nullptr;
   int rc = nws_reverb_get_plan(ctx, L, s, &pl);
@@ -262,9 +381,19 @@ int nws_launch_reverb(NwsContext* ctx, const float* x, float* out, float2* work,
   const int n_pairs = (B + 1) / 2, W = pl->cols_per_cta;
   rc = launch_cols_fwd(ctx, pl, x, B, N, work, s);
   if (rc) return rc;
-  nws_reverb_rows_kernel<<<dim3(pl->n1 / 2, n_pairs), 256, 0, s>>>(work, pl->ir_spec, ctx->tw_master, pl->n1, 0);
+  nws_reverb_rows_kernel<<<dim3((pl->n1 + 1) / 2, n_pairs), 256, 0, s>>>(work, pl->ir_spec, ctx->tw_master, pl->n1, 0);
   NWS_LAUNCH_CHECK();
-  const int Lc = N > kReverbIr ? N : kReverbIr;
+  if (pl->mixed) {
+    const size_t smem = cols_mixed_smem_bytes(pl->n1, W);
+    if (pl->n1 == 125)
+      nws_reverb_cols_inv_mixed_kernel<125><<<dim3(256 / W, n_pairs), 256, smem, s>>>(work, pl->tw_big, pl->tw_cols, ilog2(W), x, out, B, N);
+    else
+      nws_reverb_cols_inv_mixed_kernel<250><<<dim3(256 / W, n_pairs), 256, smem, s>>>(work, pl->tw_big, pl->tw_cols, ilog2(W), x, out, B, N);
+    NWS_LAUNCH_CHECK();
+    return NWS_OK;
+  }
+  // an exact power-of-two plan has no wrap either: a circular length beyond every index disables the fold
+  const int Lc = exact ? (1 << 30) : (N > kReverbIr ? N : kReverbIr);
   if (Lc % 256 == 0) {
     // (x + y*scale: the scale is applied to the sum y[n] + y[n+Lc] — same value up to one rounding)
     nws_reverb_cols_inv_kernel<true><<<dim3(256 / W, n_pairs), 256, cols_smem_bytes(pl->n1, W), s>>>(

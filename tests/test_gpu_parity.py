@@ -215,7 +215,10 @@ def test_noise_branch(tag, eng_rand, eng_vn):
     assert e[0] < 2e-5 * max(1.0, float(ref.abs().max())), (e, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("tag,N", [("randinit", 768), ("vn", 1280), ("vn", 4096), ("vn", 32000), ("vn", 33024), ("vn", 64000)])
+# 768 .. 32000: exact-length plan 125 x 256; 32768: exact 128 x 256; 33024, 96000: zero-padded power-of-two plan
+# with the wrap folded back; 64000: exact 250 x 256 (the benchmark configs)
+@pytest.mark.parametrize("tag,N", [("randinit", 768), ("vn", 1280), ("vn", 4096), ("vn", 32000), ("vn", 32768),
+                                   ("vn", 33024), ("vn", 64000), ("vn", 96000)])
 def test_reverb(tag, N, eng_rand, eng_vn):
     eng, w = eng_rand if tag == "randinit" else eng_vn
     gen = torch.Generator().manual_seed(N)

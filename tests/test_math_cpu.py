@@ -143,3 +143,25 @@ def test_philox_known_answer_and_uniformity(lib):
     lib.h_philox(ctypes.c_uint64(1234), ctypes.c_uint64(1), ctypes.c_uint64(0), ctypes.c_long(50000), _p(out))
     assert out.min() >= 0.0 and out.max() < 1.0
     assert abs(out.mean() - 0.5) < 5e-3 and abs(out.var() - 1 / 12) < 2e-3
+
+
+@pytest.mark.parametrize("n1", [125, 250])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_mixed_radix_column_fft_matches_numpy(n1, inverse):
+    """csrc/nws_fft_mixed.cuh (the column transforms of the reverb's exact-length plans: 32000 = 125 x 256,
+    64000 = 250 x 256) run serially on the CPU against numpy's FFT in float64."""
+    out_so = os.path.join(tempfile.mkdtemp(prefix="nws_fft_"), "libfft_harness.so")
+    src = os.path.join(HERE, "cpu_harness", "fft_harness.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-shared", "-fPIC", "-o", out_so, src])
+    L = ctypes.CDLL(out_so)
+    rng = np.random.default_rng(n1 + inverse)
+    tw = np.exp(-2j * np.pi * np.arange(n1) / n1).astype(np.complex64)
+    for log_w in (0, 3, 4):
+        W = 1 << log_w
+        x = (rng.standard_normal((n1, W)) + 1j * rng.standard_normal((n1, W))).astype(np.complex64)
+        out = np.zeros_like(x)
+        assert L.h_fft_mixed(n1, inverse, log_w, _p(x), _p(tw), _p(out)) == 0
+        x64 = x.astype(np.complex128)
+        ref = np.fft.ifft(x64, axis=0) * n1 if inverse else np.fft.fft(x64, axis=0)
+        assert np.abs(out - ref).max() < 4e-7 * np.abs(ref).max()
+    assert L.h_fft_mixed(128, 0, 0, _p(x), _p(tw), _p(out)) == -1
