@@ -180,25 +180,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     // polling an mbarrier here cost 15 % of the SM's issue slots — issues the 3xTF32 MMAs of the stage and
     // commits to the stage's free barrier; the last stage's commit also tells the warpgroup its accumulator is
     // complete.
-    const int w = wwarp;
-    const uint32_t acc = tmem_base_s + w * C::kTmemColsWg;
+    // Everything the MMAs take (tensor-memory addresses, descriptors) is made provably warp-uniform (a lane-0
+    // broadcast, as CUTLASS's canonical_warp_idx_sync does) and the stage loop is fully unrolled, so the operands
+    // live in uniform registers and the descriptor of every k-step is base + immediate: without this the compiler
+    // wrapped each of the 39 MMAs of a tile in a 19-instruction elect / R2UR / vote loop (8 % of the SM's issue
+    // slots went to the four MMA warps).
+    const int w = __shfl_sync(0xffffffffu, wwarp, 0);
+    const uint32_t acc = __shfl_sync(0xffffffffu, tmem_base_s, 0) + w * C::kTmemColsWg;
     const uint64_t dbh0 = nws_umma_smem_desc(w_hi_addr, kLboB, kSbo), dbl0 = nws_umma_smem_desc(w_lo_addr, kLboB, kSbo);
-    bool more = true;
-    while (more) {   // one iteration per tile of warpgroup w; tiles are handed out dynamically
-#pragma unroll 1
+    const bool issuer = nws_elect_one();
+    for (;;) {   // one iteration per tile of warpgroup w; tiles are handed out dynamically
+      fill_wait(w, 0);
+      if (done_s[w]) break;   // woken by the warpgroup running out of tiles
+#pragma unroll
       for (int st = 0; st < C::NST; ++st) {
         const int buf = st & 1;
-        fill_wait(w, buf);
-        if (st == 0 && done_s[w]) { more = false; break; }   // woken by the warpgroup running out of tiles
+        if (st > 0) fill_wait(w, buf);
         nws_tc_fence_after();
-        if (lane == 0) {
-          const int k0 = st * C::KS;
-          const int ks_here = (kHarmPad - k0) < C::KS ? (kHarmPad - k0) : C::KS;
+        if (issuer) {
+          const int ks_here = (kHarmPad - st * C::KS) < C::KS ? (kHarmPad - st * C::KS) : C::KS;
           const uint32_t a_hi = acc + C::kColA + buf * 2 * C::KS, a_lo = a_hi + C::KS;   // A operand: tensor memory
+#pragma unroll
           for (int j = 0; j < ks_here / 8; ++j) {
             // one k-step (8 harmonics) further down the weight tile = 2 * kLboB bytes = +128 in the descriptor's
             // start-address field (16-byte units; the field cannot carry: shared memory is < 2^18 bytes)
-            const uint64_t adv = (uint64_t)((k0 / 8 + j) * (2 * kLboB / 16));
+            const uint64_t adv = (uint64_t)((st * C::KS / 8 + j) * (2 * kLboB / 16));
             umma_tf32_ts(acc, a_hi + j * 8, dbh0 + adv, idesc, (st | j) ? 1u : 0u);
             umma_tf32_ts(acc, a_lo + j * 8, dbh0 + adv, idesc, 1u);
             umma_tf32_ts(acc, a_hi + j * 8, dbl0 + adv, idesc, 1u);

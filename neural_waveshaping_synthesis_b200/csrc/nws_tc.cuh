@@ -67,6 +67,17 @@ __device__ __forceinline__ bool nws_mbar_wait(uint64_t* bar, uint32_t parity, ui
   return false;
 }
 
+// one lane of the (converged) warp, chosen by the hardware: the issuing thread of the MMA warps
+__device__ __forceinline__ bool nws_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void nws_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void nws_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
