@@ -152,43 +152,52 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
       if (!ok) fault_s = 1;
     }
   } else if (warp == 5) {
-    // ================= MMA issuer
-    if (lane == 0) {
+    // ================= MMA issuer: the whole warp walks the block sequence (waits included) with warp-uniform
+    // operands — tensor-memory base broadcast from lane 0, descriptors from kernel parameters and constants — and
+    // one elected lane issues, so the MMAs go out back to back from uniform registers (a lone lane-0 thread made
+    // the compiler wrap every MMA in an elect / R2UR / vote loop, about as long as the MMA itself).
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const bool issuer = nws_elect_one();
       uint32_t n_use = 0, a_ver = 0, n_blk = 0;
       bool ok = true;
       for (int tile = item0; tile < n_tiles && ok; tile += item_step) {
         for (int b = b_begin; b < b_end && ok; ++b, ++n_blk) {
           const MlpBlockDesc d = p.blk[b];
           if (d.new_a) {   // wait for the epilogue warpgroup to publish this block's A
-            ok = nws_mbar_wait(&a_ready, a_ver & 1);
+            ok = __all_sync(0xffffffffu, nws_mbar_wait(&a_ready, a_ver & 1));
             ++a_ver;
             if (!ok) break;
           }
           nws_tc_fence_after();
           const uint32_t idesc = nws_umma_idesc_tf32(128, d.n);
           const uint32_t lbo = (uint32_t)(d.n / 8) * 128u, part = (uint32_t)d.n * kChunkK * 4u;
-          const uint32_t dcol = tmem + kColD + (n_blk & 1) * 128;
+          const uint32_t dcol = tmem_u + kColD + (n_blk & 1) * 128;
           for (int ck = 0; ck < kEmb / kChunkK && ok; ++ck, ++n_use) {
             const int s = n_use % kSlots;
-            ok = nws_mbar_wait(&full_bar[s], (n_use / kSlots) & 1);
+            ok = __all_sync(0xffffffffu, nws_mbar_wait(&full_bar[s], (n_use / kSlots) & 1));
             if (!ok) break;
             nws_tc_fence_after();
             const uint32_t sb = nws_smem_u32(smem + s * kSlotBytes);
+            if (issuer) {
 #pragma unroll
-            for (int j = 0; j < kChunkK / 8; ++j) {
-              const uint32_t acol = ck * kChunkK + j * 8;
-              const uint64_t bh = nws_umma_smem_desc(sb + j * 2 * lbo, lbo, 128);
-              const uint64_t bl = nws_umma_smem_desc(sb + part + j * 2 * lbo, lbo, 128);
-              umma_tf32_ts(dcol, tmem + kColAhi + acol, bh, idesc, (ck | j) ? 1u : 0u);
-              umma_tf32_ts(dcol, tmem + kColAlo + acol, bh, idesc, 1u);
-              umma_tf32_ts(dcol, tmem + kColAhi + acol, bl, idesc, 1u);
+              for (int j = 0; j < kChunkK / 8; ++j) {
+                const uint32_t acol = ck * kChunkK + j * 8;
+                const uint64_t bh = nws_umma_smem_desc(sb + j * 2 * lbo, lbo, 128);
+                const uint64_t bl = nws_umma_smem_desc(sb + part + j * 2 * lbo, lbo, 128);
+                umma_tf32_ts(dcol, tmem_u + kColAhi + acol, bh, idesc, (ck | j) ? 1u : 0u);
+                umma_tf32_ts(dcol, tmem_u + kColAlo + acol, bh, idesc, 1u);
+                umma_tf32_ts(dcol, tmem_u + kColAhi + acol, bl, idesc, 1u);
+              }
+              nws_umma_commit(&empty_bar[s]);   // slot reusable once these MMAs have read it
             }
-            nws_umma_commit(&empty_bar[s]);   // slot reusable once these MMAs have read it
+            __syncwarp();
           }
-          if (ok) nws_umma_commit(&d_ready[n_blk & 1]);
+          if (ok && issuer) nws_umma_commit(&d_ready[n_blk & 1]);
+          __syncwarp();
         }
       }
-      if (!ok) fault_s = 1;
+      if (!ok && lane == 0) fault_s = 1;
     }
   } else {
     // ================= epilogue warpgroup: thread = frame row = TMEM lane
