@@ -39,7 +39,7 @@ ALGO_BYTES_PER_UTT_FRAME = 4 + 8 + 512   # f0 (1 fp32) + control (2 fp32) read, 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="fastnewt", choices=["fastnewt", "newt"])
@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -105,7 +105,7 @@ def build_weights():
     return NeuralWaveshaping().eval()
 
 
-def cpu_reference_throughput(model, variant: str, T: int, batch: int, steps: int, warmup: int):
+def cpu_reference_throughput(model, variant: str, T: int, batch: int, steps: int, warmup: int, budget_s=None):
     """Times the oracle port (reference op sequence, torch CPU, all host threads).  Returns
     (samples_per_s, ms_per_step, threads)."""
     import torch
@@ -116,6 +116,7 @@ def cpu_reference_throughput(model, variant: str, T: int, batch: int, steps: int
     f0 = torch.rand(batch, 1, T)
     control = torch.rand(batch, 2, T)
     times = []
+    t_start = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         u, noise = oracle.draw_rng(T)
@@ -123,7 +124,10 @@ def cpu_reference_throughput(model, variant: str, T: int, batch: int, steps: int
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        if budget_s is not None and times and time.perf_counter() - t_start > budget_s:
+            break   # bounded: the CPU arm must end within minutes whatever K is (steps actually timed are reported)
     mean = sum(times) / len(times)
+    cpu_reference_throughput.steps_timed = len(times)
     return batch * T * HOP / mean, mean * 1e3, torch.get_num_threads()
 
 
@@ -161,14 +165,14 @@ def run_reference(args):
         if best is None or probe > best[0]:
             best = (probe, threads)
     torch.set_num_threads(best[1])
-    sps, ms, threads = cpu_reference_throughput(model, args.variant, T, args.cpu_batch, args.steps, args.warmup)
+    sps, ms, threads = cpu_reference_throughput(model, args.variant, T, args.cpu_batch, args.steps, args.warmup, budget_s=120.0)
     sample = ("oracle port of NeuralWaveshaping.forward (%s, faithful _lookup loop), %d of the %d utterances per step, "
               "%g s each, torch CPU %d threads" % (args.variant, args.cpu_batch, args.batch_per_gpu * args.gpus,
                                                   args.seconds, threads))
     line = {
         "impl": "reference", "metric": "audio samples/sec", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps": args.steps, "steps_timed": cpu_reference_throughput.steps_timed, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rtf_per_utterance": (ms / 1e3) / (args.cpu_batch * args.seconds),
         "config": workload_config(args),
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},

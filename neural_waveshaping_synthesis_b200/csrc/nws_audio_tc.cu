@@ -337,9 +337,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
             float h[8], l[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL((float)(k0 + kk + j + 1), phase), sm_shift[k0 + kk + j]));
-              h[j] = nws_tf32_hi(s);
-              l[j] = s - h[j];
+              if (k0 + kk + j < kHarm) {
+                const float s = NWS_OSC_SIN(NWS_ADD(NWS_MUL((float)(k0 + kk + j + 1), phase), sm_shift[k0 + kk + j]));
+                h[j] = nws_tf32_hi(s);
+                l[j] = s - h[j];
+              } else {   // harmonics 102..104 are padding (zero mixer weights): no sine
+                h[j] = 0.f;
+                l[j] = 0.f;
+              }
             }
             tmem_st8(col_hi + kk, h);
             tmem_st8(col_lo + kk, l);

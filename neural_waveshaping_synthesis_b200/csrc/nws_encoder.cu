@@ -85,10 +85,16 @@ nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, c
   __shared__ float pre_rz[2 * kEmb];
   __shared__ float pre_ni[kEmb], pre_nh[kEmb];
 
-  float4 w[32];
+  // rows j and j|16 are kept as packed pairs so one fma.rn.f32x2 (FFMA2) advances both dot products: 64 packed
+  // FMAs per step instead of 128 scalar ones; each element still goes through the same x, y, z, w fma chain
+  float2 wp[16][4];
 #pragma unroll
-  for (int j = 0; j < 32; ++j)
-    w[j] = *reinterpret_cast<const float4*>(w_hh + (size_t)(row0 + (j ^ lane)) * kEmb + 4 * lane);
+  for (int j = 0; j < 16; ++j) {
+    const float4 lo = *reinterpret_cast<const float4*>(w_hh + (size_t)(row0 + (j ^ lane)) * kEmb + 4 * lane);
+    const float4 hi = *reinterpret_cast<const float4*>(w_hh + (size_t)(row0 + ((j | 16) ^ lane)) * kEmb + 4 * lane);
+    wp[j][0] = make_float2(lo.x, hi.x); wp[j][1] = make_float2(lo.y, hi.y);
+    wp[j][2] = make_float2(lo.z, hi.z); wp[j][3] = make_float2(lo.w, hi.w);
+  }
   const float wi0 = w_ih[r * 2], wi1 = w_ih[r * 2 + 1], bi = b_ih[r], bh = b_hh[r];
   const float* c0 = control + (size_t)b * ctrl_channels * T;
   const float* c1 = c0 + T;
@@ -104,10 +110,14 @@ nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, c
     const float4 hv = *reinterpret_cast<const float4*>(h + 4 * lane);
     float v[16];
 #pragma unroll
+    const float2 hx = make_float2(hv.x, hv.x), hy = make_float2(hv.y, hv.y), hz = make_float2(hv.z, hv.z), hw = make_float2(hv.w, hv.w);
+#pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float a = fmaf(w[j].w, hv.w, fmaf(w[j].z, hv.z, fmaf(w[j].y, hv.y, w[j].x * hv.x)));
-      const float c = fmaf(w[j | 16].w, hv.w, fmaf(w[j | 16].z, hv.z, fmaf(w[j | 16].y, hv.y, w[j | 16].x * hv.x)));
-      v[j] = a + __shfl_xor_sync(0xffffffffu, c, 16);
+      float2 ac = __fmul2_rn(wp[j][0], hx);   // (.x: row j ^ lane, .y: row (j | 16) ^ lane)
+      ac = __ffma2_rn(wp[j][1], hy, ac);
+      ac = __ffma2_rn(wp[j][2], hz, ac);
+      ac = __ffma2_rn(wp[j][3], hw, ac);
+      v[j] = ac.x + __shfl_xor_sync(0xffffffffu, ac.y, 16);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j | 8], 8);

@@ -1,0 +1,21 @@
+# Round evidence run on one B200 (gpurun): tests, bench lines, launch list, ncu captures, parity report.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem --format=csv > gpurun_out/smi.txt; nproc >> gpurun_out/smi.txt
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/pytest.log
+timeout 600 python bench.py > gpurun_out/bench_fast.json 2> gpurun_out/bench_fast.err; tail -c 300 gpurun_out/bench_fast.err
+timeout 300 python bench.py --steps 50 --warmup 3 --variant newt --no-cpu-baseline > gpurun_out/bench_newt.json 2> gpurun_out/bench_newt.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
+# the 11th launch of the audio kernel is the first serial, whole-utterance one (5 pipelined forwards = 10 launches before it)
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:nws_audio_tc_kernel -s 10 -c 1 -f -o gpurun_out/audio_lut python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_audio.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:nws_audio_tc_kernel -s 10 -c 1 -f -o gpurun_out/audio_mlp python bench.py --steps 2 --warmup 3 --variant newt --no-cpu-baseline > gpurun_out/ncu_audio_mlp.log 2>&1
+timeout 300 python scripts/parity_report.py --json gpurun_out/parity.json 2>&1 | tail -3
+python - <<'P'
+import json
+for f in ("bench_fast", "bench_newt", "bench_ref"):
+    try:
+        d = json.loads(open("gpurun_out/%s.json" % f).read())
+        print(f, d.get("ms_per_step"), d.get("value"), d.get("e2e"), d.get("clocks"), (d.get("roofline") or {}).get("kernel_ms"), d.get("stages_ms"), d.get("cpu_baseline"))
+    except Exception as e:
+        print(f, "FAILED", e)
+P
