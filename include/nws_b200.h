@@ -239,6 +239,28 @@ int nws_stream_push(NwsStreamHandle stream_state, const float* f0, const float* 
                     int n_frames, const float* noise_window, int use_lut, int flush, int apply_reverb, float* out,
                     int* n_out_frames, void* stream);
 
+/* ---- control-side feature extraction: what produces control channel 1 of the forward
+ * in the timbre-transfer use case (colab cell 14, scripts/create_dataset.py).  No handle: these do not depend on
+ * the model.  All of the reference's arithmetic here is librosa 0.8.0's (requirements.txt:5).
+ *
+ * Replaces: extract_perceptual_loudness / compute_power_spectrogram / perform_perceptual_weighting
+ * (neural_waveshaping_synthesis/data/utils/loudness_extraction.py:43-68, :11-23, :26-40) for a batch of B
+ * segments of N samples: centred reflect-padded STFT (periodic Hann window, n_fft a power of two 64..4096,
+ * float64 transform stored as complex64 like librosa.stft), amplitude_to_db(ref=max over the segment,
+ * amin=epsilon, top_db=80), mean over the n_fft/2+1 bins (the A-weighting is computed but not added by the
+ * reference, :39), and (x + 80) / 80 when normalise != 0.
+ *   audio        [B, N]                     loudness_out [B, 1 + N / hop_length]
+ *   db_out       optional [B, 1 + N / hop_length, n_fft / 2 + 1] (frame-major): the dB spectrogram that
+ *                compute_power_spectrogram returns (transposed)
+ * N > n_fft / 2 (the reflect padding needs it).                                                            */
+size_t nws_loudness_workspace_bytes(int B, int N, int n_fft, int hop_length);
+int nws_extract_loudness(const float* audio, int B, int N, int n_fft, int hop_length, double epsilon,
+                         int normalise, float* loudness_out, float* db_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* Replaces: extract_rms (loudness_extraction.py:71-90): zero-padded centred frames of window_size every
+ * hop_length, sqrt(mean(x^2)).  audio [B, N] -> rms_out [B, 1 + (N + 2*(window_size/2) - window_size) / hop_length]. */
+int nws_extract_rms(const float* audio, int B, int N, int window_size, int hop_length, float* rms_out, void* stream);
+
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 uint64_t nws_launch_count(int reset);

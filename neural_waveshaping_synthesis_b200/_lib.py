@@ -117,6 +117,12 @@ def load_library():
         L.nws_stream_push.argtypes = [vp, vp, vp, c_int, c_int, vp, c_int, c_int, c_int, vp, POINTER(c_int), vp]
         for name in ("nws_stream_create", "nws_stream_destroy", "nws_stream_reset", "nws_stream_window", "nws_stream_push"):
             getattr(L, name).restype = c_int
+        L.nws_loudness_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        L.nws_loudness_workspace_bytes.restype = c_size_t
+        L.nws_extract_loudness.argtypes = [vp, c_int, c_int, c_int, c_int, ctypes.c_double, c_int, vp, vp, vp, c_size_t, vp]
+        L.nws_extract_loudness.restype = c_int
+        L.nws_extract_rms.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp]
+        L.nws_extract_rms.restype = c_int
         L.nws_shaper_eval_scratch_bytes.restype = c_size_t
         L.nws_shaper_eval.argtypes = [POINTER(vp), vp, vp, c_int, vp, vp]
         for name in ("nws_create", "nws_destroy", "nws_load_weights", "nws_build_lut", "nws_set_lut", "nws_get_lut",
@@ -140,6 +146,7 @@ EXPORTED_SYMBOLS = [
     "nws_reverb_workspace_bytes", "nws_shaper_eval_scratch_bytes", "nws_shaper_eval", "nws_launch_count",
     "nws_set_profiling", "nws_get_stage_times", "nws_selftest_umma", "nws_set_audio_impl", "nws_set_mlp_impl", "nws_stage_control_to_params", "nws_selftest_sin", "nws_set_pipeline",
     "nws_stream_create", "nws_stream_destroy", "nws_stream_reset", "nws_stream_window", "nws_stream_push",
+    "nws_loudness_workspace_bytes", "nws_extract_loudness", "nws_extract_rms",
 ]
 STAGE_NAMES = ["rng", "phase_carry", "gru", "proj", "film_mlp", "noise_mlp", "noise_spectrum", "noise_filter",
                "audio_fused", "reverb"]

@@ -23,3 +23,19 @@ int h_fft_mixed(int n1, int inverse, int log_w, const float* in, const float* tw
   return z ? 0 : -1;
 }
 }
+
+#include "../../neural_waveshaping_synthesis_b200/csrc/nws_fft_f64.cuh"
+
+extern "C" {
+// One forward transform of length 1 << log_n, complex128, natural order.  tw = exp(-2*pi*i*m/N), m < N/2.
+void h_fft_f64(int log_n, const double* in, const double* tw, double* out) {
+  const size_t n = (size_t)1 << log_n;
+  double2* a = (double2*)malloc(n * sizeof(double2));
+  double2* b = (double2*)malloc(n * sizeof(double2));
+  memcpy(a, in, n * sizeof(double2));
+  double2* z = nws_fft_f64(a, b, (const double2*)tw, log_n, 0, 1);
+  memcpy(out, z, n * sizeof(double2));
+  free(a);
+  free(b);
+}
+}

@@ -1,0 +1,80 @@
+"""CPU tests of the loudness-extraction oracle (oracle/loudness_oracle.py, a restatement of librosa 0.8.0's
+stft / amplitude_to_db as used by the reference's data/utils/loudness_extraction.py) and of the float64 FFT
+header the CUDA extractor uses.  librosa is absent, so the oracle is cross-checked against an independent STFT
+(torch.stft, float64) rather than pinned to reference outputs — see the oracle's header."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loudness_oracle as lo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _signal(n, seed=0, sr=16000):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / sr
+    f0 = 220.0 * 2 ** (0.3 * np.sin(2 * np.pi * 1.3 * t))
+    phase = 2 * np.pi * np.cumsum(f0) / sr
+    env = 0.5 * (1 - np.cos(2 * np.pi * np.minimum(t / t[-1], 1.0))) * 0.4
+    x = env * sum(np.sin(k * phase) / k for k in range(1, 9)) + 1e-3 * rng.standard_normal(n)
+    return x.astype(np.float32)
+
+
+@pytest.mark.parametrize("n,n_fft,hop", [(64000, 1024, 128), (16000, 2048, 512), (5000, 256, 100)])
+def test_stft_restatement_matches_torch_stft(n, n_fft, hop):
+    x = _signal(n)
+    S = lo.stft(x, n_fft, hop)
+    assert S.dtype == np.complex64 and S.shape == (n_fft // 2 + 1, 1 + n // hop)
+    ref = torch.stft(torch.from_numpy(x).double(), n_fft, hop_length=hop,
+                     window=torch.hann_window(n_fft, periodic=True, dtype=torch.float64),
+                     center=True, pad_mode="reflect", return_complex=True).numpy()
+    assert np.abs(S - ref).max() <= 2e-7 * np.abs(ref).max()
+
+
+def test_db_spectrogram_properties_and_edge_cases():
+    x = _signal(16000, seed=1)
+    db = lo.compute_power_spectrogram(x, 1024, 128, "hann", 1e-5)
+    assert db.dtype == np.float32 and db.max() == 0.0 and db.min() >= -80.0
+    loud = lo.extract_perceptual_loudness(x, n_fft=1024, hop_length=128, interpolate_fn=None)
+    assert loud.shape == (126,) and np.all(loud >= 0.0) and np.all(loud <= 1.0)
+    # digital silence: every bin sits at amin, i.e. at the maximum -> 0 dB everywhere -> normalised loudness 1
+    silent = lo.extract_perceptual_loudness(np.zeros(4096, np.float32), n_fft=1024, hop_length=128, interpolate_fn=None)
+    assert np.all(silent == 1.0)
+    # the interpolated variant has one value per audio sample
+    up = lo.extract_perceptual_loudness(x, n_fft=1024, hop_length=128)
+    assert up.shape == (16000,)
+    r = lo.extract_rms(x, 1024, 256, interpolate_fn=None)
+    assert r.shape == (1 + 16000 // 256,) and r.max() < 1.0
+
+
+def test_f64_fft_header_matches_numpy():
+    out_so = os.path.join(tempfile.mkdtemp(prefix="nws_fft_"), "libfft_harness.so")
+    src = os.path.join(HERE, "cpu_harness", "fft_harness.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-shared", "-fPIC", "-o", out_so, src])
+    L = ctypes.CDLL(out_so)
+    P = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(3)
+    for log_n in range(1, 13):
+        n = 1 << log_n
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        tw = np.exp(-2j * np.pi * np.arange(max(n // 2, 1)) / n)
+        out = np.zeros_like(x)
+        L.h_fft_f64(log_n, x.ctypes.data_as(P), tw.ctypes.data_as(P), out.ctypes.data_as(P))
+        ref = np.fft.fft(x)
+        assert np.abs(out - ref).max() <= 2e-15 * np.abs(ref).max() * log_n
+
+
+def test_mirror_has_no_cpu_fallback():
+    from neural_waveshaping_synthesis.data.utils.loudness_extraction import extract_perceptual_loudness, perceptual_loudness_batch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError):
+        extract_perceptual_loudness(np.zeros(4096, np.float32))
+    with pytest.raises(ValueError):
+        perceptual_loudness_batch(torch.zeros(1, 4096))
