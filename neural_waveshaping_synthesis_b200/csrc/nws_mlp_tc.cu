@@ -416,8 +416,17 @@ int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, flo
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   const int tiles = (M / p.T) * ((p.t_end - p.t_begin + 127) / 128);
-  p.split = 2 * tiles <= ctx->sm_count ? 1 : 0;   // few tiles: halve the dependent-block chain per CTA (latency)
-  const int grid = p.split ? 2 * tiles : (tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  // A tile's block sequence is two self-contained halves (proj + FiLM chain | proj + noise chain).  Handing out
+  // half-tiles halves the dependent chain per CTA when there are few tiles (latency) and shortens the last wave
+  // otherwise: 192 tiles (the pipelined forward's second block) are 2 rounds of whole tiles on 148 SMs but
+  // 3 rounds of half tiles = 1.5.  Split whenever it takes strictly fewer tile-times.
+  const int sms_even = ctx->sm_count & ~1;
+  const int grid_whole = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  const int grid_split = 2 * tiles < sms_even ? 2 * tiles : sms_even;
+  const int rounds_whole2 = 2 * ((tiles + grid_whole - 1) / grid_whole);   // in half-tile times
+  const int rounds_split2 = (2 * tiles + grid_split - 1) / grid_split;
+  p.split = rounds_split2 < rounds_whole2 ? 1 : 0;
+  const int grid = p.split ? grid_split : grid_whole;
   nws_mlp_tc_kernel<<<grid, kMlpThreads, smem, s>>>(p, nullptr);
   NWS_LAUNCH_CHECK();
   return NWS_OK;

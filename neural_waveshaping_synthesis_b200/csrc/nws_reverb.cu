@@ -295,8 +295,14 @@ void nws_reverb_free_plans(NwsContext* ctx) {
   ctx->n_plans = 0;
 }
 
+// Columns per CTA of the mixed-radix column kernels, chosen per launch so the grid is one balanced wave:
+// 8 columns = 32 KB of ping-pong buffers -> 7 CTAs per SM = 1036 slots for the 1024 CTAs of a 64-utterance batch
+// (16 columns gave 512 CTAs on 444 slots: a second wave 13 % full); 4 columns for a handful of utterances, where
+// the number of CTAs in flight is what bounds the latency.
+static int mixed_cols(int n_pairs) { return n_pairs <= 4 ? 4 : 8; }
+
 static int launch_cols_fwd(NwsContext* ctx, NwsReverbPlan* pl, const float* x, int B, int N, float2* work, cudaStream_t s) {
-  const int W = pl->cols_per_cta;
+  const int W = pl->mixed ? mixed_cols((B + 1) / 2) : pl->cols_per_cta;
   dim3 grid(256 / W, (B + 1) / 2);
   if (pl->mixed) {
     const size_t smem = cols_mixed_smem_bytes(pl->n1, W);
@@ -323,7 +329,7 @@ int nws_reverb_get_plan(NwsContext* ctx, int fft_len, cudaStream_t s, NwsReverbP
     pl->n1 = n1;
     pl->mixed = n1 == 125 || n1 == 250;
     for (pl->log_n1 = 0; (1 << pl->log_n1) < n1; ++pl->log_n1) {}
-    pl->cols_per_cta = pl->mixed ? 16 : pick_cols(n1);   // mixed: 2 x 31.25 KB (n1 = 250) of ping-pong buffers per CTA
+    pl->cols_per_cta = pl->mixed ? 8 : pick_cols(n1);    // (mixed plans choose per launch: mixed_cols)
     const size_t L = (size_t)fft_len;
     if (pl->mixed) {
       float2 hc[250];
@@ -378,7 +384,7 @@ int nws_launch_reverb(NwsContext* ctx, const float* x, float* out, float2* work,
   NwsReverbPlan* pl = nullptr;
   int rc = nws_reverb_get_plan(ctx, L, s, &pl);
   if (rc) return rc;
-  const int n_pairs = (B + 1) / 2, W = pl->cols_per_cta;
+  const int n_pairs = (B + 1) / 2, W = pl->mixed ? mixed_cols(n_pairs) : pl->cols_per_cta;
   rc = launch_cols_fwd(ctx, pl, x, B, N, work, s);
   if (rc) return rc;
   nws_reverb_rows_kernel<<<dim3((pl->n1 + 1) / 2, n_pairs), 256, 0, s>>>(work, pl->ir_spec, ctx->tw_master, pl->n1, 0);

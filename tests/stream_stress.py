@@ -1,4 +1,4 @@
-"""Determinism stress of the streaming path: the same chunked run repeated, every repetition must be bit-identical."""
+"""Test tool (run by hand: python tests/stream_stress.py [reps]).  Determinism stress of the streaming path: the same chunked run repeated, every repetition must be bit-identical."""
 import os
 import sys
 
