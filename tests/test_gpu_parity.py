@@ -312,6 +312,28 @@ def test_full_size_batch_properties():
     assert e[0] < TOL_CKPT_MAX and e[1] < TOL_CKPT_RMS, e
 
 
+def test_c5_shard_of_256_utterances():
+    """BASELINE configs[4]: 2048 utterances over 8 GPUs = 256 x 4 s per GPU.  More utterances than SMs: the GRU runs
+    in two waves and the forward takes the serial (non-pipelined) order — rows must equal the same utterances
+    rendered in a 64-utterance batch (pipelined order) to fp32 round-off, and one row is checked against the oracle."""
+    m, w = _model("vn", True)
+    f0, control = oracle.realistic_inputs(500, w["data_mean"].numpy(), w["data_std"].numpy(), B=1)
+    gen = torch.Generator().manual_seed(9)
+    f0b = (f0 * (0.4 + 1.2 * torch.rand(256, 1, 1, generator=gen))).contiguous()
+    cb = (control + 0.1 * torch.randn(256, 2, 1, generator=gen)).contiguous()
+    u, noise = oracle.draw_rng(500, 3)
+    args = dict(phase_shift=u.reshape(-1).cuda(), noise=noise.cuda())
+    with torch.no_grad():
+        y = m(f0b.cuda(), cb.cuda(), **args)
+        assert y.shape == (256, 64000) and torch.isfinite(y).all()
+        y64 = m(f0b[128:192].cuda(), cb[128:192].cuda(), **args)
+        ref = oracle.forward(w, f0b[255:256], cb[255:256], u, noise, lut=oracle.build_lookup_table(w))
+    for i in (0, 31, 63):
+        assert err(y64[i], y[128 + i])[0] < 2e-6 * float(y64[i].abs().max()), i
+    e = err(y[255:256], ref)
+    assert e[0] < TOL_CKPT_MAX and e[1] < TOL_CKPT_RMS, e
+
+
 def test_long_utterance_other_fft_plan():
     """12 s utterances (T=1500, N=192000): another reverb transform length (L = 2^18), oscillator arguments up
     to ~6e5 rad, phase carries deep into the fp64 scan — against the oracle."""
