@@ -10,6 +10,9 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:nws_audio_tc_kernel -s 10 -c 1 -f -o gpurun_out/audio_lut python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_audio.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:nws_audio_tc_kernel -s 10 -c 1 -f -o gpurun_out/audio_mlp python bench.py --steps 2 --warmup 3 --variant newt --no-cpu-baseline > gpurun_out/ncu_audio_mlp.log 2>&1
 timeout 300 python scripts/parity_report.py --json gpurun_out/parity.json 2>&1 | tail -3
+PYTHONPATH=. timeout 300 python scripts/dev_sweep.py > gpurun_out/sweep.log 2>&1; tail -2 gpurun_out/sweep.log
+PYTHONPATH=. timeout 300 python scripts/time_streaming.py --json gpurun_out/streaming.json > gpurun_out/streaming.log 2>&1; tail -2 gpurun_out/streaming.log
+PYTHONPATH=. timeout 300 python scripts/time_loudness.py --json gpurun_out/loudness.json 2>&1 | tail -1
 python - <<'P'
 import json
 for f in ("bench_fast", "bench_newt", "bench_ref"):
