@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--cpu-batch", type=int, default=8, help="utterances per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inputs", default="rand", choices=["rand", "realistic"],
+                    help="rand = the reference timing scripts' torch.rand f0/control (the contract's workload); "
+                         "realistic = violin checkpoint + vibrato around 110-660 Hz (SURVEY.md 8(d)'s second input set)")
     return ap.parse_args()
 
 
@@ -215,7 +218,10 @@ def workload_config(args):
              1 if args.variant == "fastnewt" else 2),
             "variant": args.variant, "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * args.gpus,
             "seconds": args.seconds, "frames": int(SR * args.seconds) // HOP, "sample_rate": SR,
-            "inputs": "torch.rand f0/control as scripts/time_forward_pass.py:27-40; random-init newt.gin weights, seed 0",
+            "inputs": ("torch.rand f0/control as scripts/time_forward_pass.py:27-40; random-init newt.gin weights, seed 0"
+                       if getattr(args, "inputs", "rand") == "rand" else
+                       "violin checkpoint (tests/golden/weights_vn.npz); f0 = 440 Hz x 2^(0.5 sin) vibrato scaled by "
+                       "U[0.25,1.5) per utterance, loudness LFO, control normalised with the checkpoint's data_mean/std"),
             "rng": "on-device Philox draws inside the timed region", "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": "dp%d (utterance shards, no data-path collective)" % args.gpus}
 
@@ -239,6 +245,10 @@ def run_b200(args):
     from neural_waveshaping_synthesis_b200 import _lib
     import copy
     cpu_model = build_weights()
+    if args.inputs == "realistic":            # the violin checkpoint instead of the random-init weights
+        import numpy as np
+        zw = np.load(os.path.join(REPO, "tests", "golden", "weights_vn.npz"))
+        cpu_model.load_state_dict({k: torch.from_numpy(zw[k]) for k in zw.files if not k.startswith("data_")})
     model = copy.deepcopy(cpu_model)          # .to() moves a module in place: keep the CPU copy apart
     if args.variant == "fastnewt":
         model.newt = FastNEWT(model.newt)
@@ -246,8 +256,20 @@ def run_b200(args):
     B, T = args.batch_per_gpu, int(SR * args.seconds) // HOP
     N = T * HOP
     torch.manual_seed(1 + rank)
-    f0_host = torch.rand(B, 1, T).pin_memory()
-    control_host = torch.rand(B, 2, T).pin_memory()
+    if args.inputs == "realistic":
+        import math
+        import numpy as np
+        z = np.load(os.path.join(REPO, "tests", "golden", "weights_vn.npz"))
+        u = torch.linspace(0, 1, T)
+        f0 = 440.0 * torch.pow(2.0, 0.5 * torch.sin(2 * math.pi * 1.5 * u)) * (0.25 + 1.25 * torch.rand(B, 1, 1))
+        loud = (0.10 + 0.03 * torch.sin(2 * math.pi * 3 * u)).view(1, 1, T).expand(B, 1, T)
+        mean, std = z["data_mean"], z["data_std"]
+        f0_host = f0.float().contiguous().pin_memory()
+        control_host = torch.cat(((f0 - float(mean[0, 0])) / float(std[0, 0]), (loud - float(mean[1, 0])) / float(std[1, 0])),
+                                 dim=1).float().contiguous().pin_memory()
+    else:
+        f0_host = torch.rand(B, 1, T).pin_memory()
+        control_host = torch.rand(B, 2, T).pin_memory()
     f0, control = f0_host.to(dev), control_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lib = _lib.load_library()

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
-timeout 300 python bench.py --steps 50 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fast.json 2> gpurun_out/bench_fast.err; tail -c 300 gpurun_out/bench_fast.err; cat gpurun_out/bench_fast.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e'], d['roofline']['kernel_ms'], d['stages_ms'])"
+for inp in rand realistic; do for ch in 1 2 4 8; do
+NWS_TILE_CHUNK=$ch timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --inputs $inp > gpurun_out/b.json 2> gpurun_out/b.err; tail -c 200 gpurun_out/b.err
+python -c "import json,sys; d=json.loads(open('gpurun_out/b.json').read()); print('$inp chunk $ch', round(d['ms_per_step'],4), round(d['e2e']['ms_per_step'],4), round(d['roofline']['kernel_ms'],4), {k:round(v,4) for k,v in d['stages_ms'].items() if v>0.03})"
+done; done
