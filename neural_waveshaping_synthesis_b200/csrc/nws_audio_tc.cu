@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     }
     }
     // the noise-branch sample that is added to the mixdown at the very end: its latency hides behind the shaper loop
-    const float noise_v = p.noise_in ? p.noise_in[(size_t)b * N + n] : 0.f;   // (aliases p.out: plain load)
+    const float noise_v = p.noise_in ? __ldcs(p.noise_in + (size_t)b * N + n) : 0.f;   // (aliases p.out: not the read-only path; streaming: read once, keep L1 for the table)
     {  // accumulator complete when the last stage's commit lands (a commit covers all earlier MMAs)
       const int lb = (C::NST - 1) & 1;
       const uint32_t u = lb ? uses1 : uses0;
