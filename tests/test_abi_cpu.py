@@ -116,3 +116,61 @@ def test_dataset_mirror(tmp_path):
     item = ds[0]
     assert item["f0"].shape == (1, 500) and item["control"].shape == (19, 500) and item["name"] == "a_0"
     assert np.allclose(item["f0"], item["control"][0:1] * std[0] + mean[0])
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/nws_b200.h is the boundary a non-C++ host binds: it must compile as strict C99 on its own, and a C
+    translation unit calling every entry point through it must compile without warnings (no torch, no C++ types)."""
+    import subprocess
+    src = tmp_path / "use_abi.c"
+    src.write_text(r"""
+#include "nws_b200.h"
+int use_abi(void* stream) {
+  NwsConfig cfg;
+  NwsHandle h = 0;
+  NwsStreamHandle st = 0;
+  int n_out = 0, frames = 0;
+  long long first = 0;
+  float ms[NWS_N_STAGES];
+  nws_default_config(&cfg);
+  if (nws_create(&cfg, &h) != NWS_OK) return nws_api_version() + (nws_last_error() != 0);
+  nws_load_weights(h, 0, NWS_T_COUNT, stream);
+  nws_build_lut(h, 4096, -3.0f, 3.0f, 0, stream);
+  nws_set_lut(h, 0, 4096, -3.0f, 3.0f, stream);
+  nws_get_lut(h, 0, stream);
+  nws_forward(h, 0, 0, 2, 0, 0, 0u, 0u, 0, 1, 2, 1, 0, nws_workspace_bytes(h, 1, 2), stream);
+  nws_forward_host(h, 0, 0, 2, 0, 0, 0u, 0u, 0, 1, 2, 1, 0, 0, stream);
+  nws_stage_control_embedding(h, 0, 2, 0, 1, 2, 0, 0, stream);
+  nws_stage_td_mlp(h, NWS_MLP_FILM, 0, 0, 1, 2, 0, 0, stream);
+  nws_stage_audio(h, 0, 0, 0, 0, 0, 1, 2, 0, 0, 0, stream);
+  nws_stage_lut_lookup(h, 0, 0, 0, 1, 256, stream);
+  nws_stage_noise(h, 0, 0, 0, 1, 2, 0, 0, stream);
+  nws_stage_reverb(h, 0, 0, 1, 256, 0, nws_reverb_workspace_bytes(h, 1, 256), stream);
+  nws_stage_control_to_params(h, 0, 2, 0, 0, 1, 2, 0, 0, stream);
+  nws_shaper_eval(0, 0, 0, 16, 0, stream);
+  nws_set_profiling(h, 1);
+  nws_get_stage_times(h, ms, NWS_N_STAGES);
+  nws_set_pipeline(h, 0);
+  nws_set_mlp_impl(h, 1);
+  nws_set_audio_impl(h, 1);
+  nws_selftest_umma(0, 0, 0, 8, 0, 0, stream);
+  nws_selftest_sin(0, 0, 0, 0, 0, stream);
+  nws_stream_create(h, 1, 8, &st);
+  nws_stream_reset(st, 0, 0u, 0u, stream);
+  nws_stream_window(st, 2, &first, &frames);
+  nws_stream_push(st, 0, 0, 2, 2, 0, 1, 0, 1, 0, &n_out, stream);
+  nws_stream_destroy(st);
+  nws_extract_loudness(0, 1, 4096, 1024, 128, 1e-5, 1, 0, 0, 0, nws_loudness_workspace_bytes(1, 4096, 1024, 128), stream);
+  nws_extract_rms(0, 1, 4096, 2048, 512, 0, stream);
+  (void)nws_shaper_eval_scratch_bytes();
+  (void)nws_launch_count(1);
+  return nws_destroy(h);
+}
+""")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(REPO, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "use_abi.o")])
+    # every function the header declares is exercised by the C file above
+    header = open(os.path.join(REPO, "include", "nws_b200.h")).read()
+    declared = set(re.findall(r"\b(nws_[a-z_0-9]+)\s*\(", header))
+    used = set(re.findall(r"\b(nws_[a-z_0-9]+)\s*\(", src.read_text()))
+    assert declared <= used, sorted(declared - used)
