@@ -199,17 +199,28 @@ def ncu_traffic(variant):
         return None
 
 
-def issue_view(variant):
+def issue_view(variant, kernel_ms=None, clocks=None, ffma_tflops=None):
     """What actually bounds the fused kernel (it is neither HBM- nor tensor-bound): warp-instruction issue.
-    Figures from the committed ncu capture of this workload (profiles/)."""
+    Instruction counts and pipe activity from the committed ncu capture of this workload (profiles/); the kernel
+    time, the SM clock and the fp32 FMA rate are measured live, so `frac_of_issue_peak` = warp-instructions per
+    second ÷ (SMs x 4 schedulers x SM clock) is this run's fraction of the issue roofline."""
     path = os.path.join(REPO, "profiles", "r1_ncu_audio_tc_%s.json" % ("lut" if variant == "fastnewt" else "mlp"))
     try:
         d = json.load(open(path))[0]
         g = lambda k: d[k]["value"]
-        return {"bound": "warp-instruction issue (fp32 SIMT epilogue + sine generation)",
-                "issue_slot_utilisation": g("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
-                "tensor_pipe_active": g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active") / 100.0,
-                "warp_instructions_per_launch": g("smsp__inst_executed.sum"), "source": os.path.basename(path)}
+        v = {"bound": "warp-instruction issue (fp32 SIMT epilogue + sine generation)",
+             "issue_slot_utilisation": g("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
+             "tensor_pipe_active": g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active") / 100.0,
+             "warp_instructions_per_launch": g("smsp__inst_executed.sum"), "source": os.path.basename(path)}
+        n_sm = int(g("launch__grid_size"))   # persistent kernel: one CTA per SM
+        if kernel_ms and clocks and clocks.get("sm_mhz"):
+            rate = v["warp_instructions_per_launch"] / (kernel_ms * 1e-3)
+            peak = n_sm * 4 * clocks["sm_mhz"] * 1e6
+            v.update({"warp_instructions_per_s": rate, "issue_peak_warp_instructions_per_s": peak,
+                      "frac_of_issue_peak": rate / peak})
+        if ffma_tflops:
+            v["fp32_ffma_tflops_measured"] = ffma_tflops
+        return v
     except Exception:
         return {"bound": "warp-instruction issue", "source": None}
 
@@ -343,6 +354,27 @@ def run_b200(args):
         e2e_s = (time.perf_counter() - t0) / args.steps
         h2d_per_step, d2h_per_step = pipe.h2d_bytes // args.steps, pipe.d2h_bytes // args.steps
 
+        # ---- fp32 FMA issue-rate probe (the compute roofline's denominator, measured on this box)
+        ffma_tflops = None
+        try:
+            import ctypes
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            probe_out = torch.empty(n_sm * 8 * 256, dtype=torch.float32, device=dev)
+            flops = ctypes.c_double(0.0)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            best = None
+            for i in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _lib.check(lib.nws_selftest_ffma_peak(probe_out.data_ptr(), n_sm * 8, 1024, ctypes.byref(flops), stream))
+                b.record()
+                torch.cuda.synchronize(dev)
+                if i > 0:
+                    best = a.elapsed_time(b) if best is None else min(best, a.elapsed_time(b))
+            ffma_tflops = flops.value / (best * 1e-3) / 1e12
+        except Exception as e:   # the probe is informative only
+            print("ffma probe failed: %s" % e, file=sys.stderr)
+
     # ---- aggregate over ranks: time = max over ranks, samples = sum
     from neural_waveshaping_synthesis_b200.sharding import aggregate_throughput
     step_ms_max, total_samples = aggregate_throughput(step_ms, float(B * N), dev)
@@ -379,7 +411,7 @@ def run_b200(args):
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": audio_ms,
                      "kernel_share_of_step": audio_ms / sum(stage_acc.values()) if stage_acc else None,
-                     "issue_view": issue_view(args.variant)},
+                     "issue_view": issue_view(args.variant, audio_ms, clocks, ffma_tflops)},
         "stages_ms": stage_acc,
     }
     if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only

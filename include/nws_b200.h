@@ -209,6 +209,11 @@ int nws_selftest_umma(const float* A, const float* B, float* D, int K, int swap_
  * the SFU-based versions (quarter-turn reduction + sin/cos select; full-turn reduction, one MUFU) on x[0..n). */
 int nws_selftest_sin(const float* x, float* y_accurate, float* y_quarter, float* y_turn, long long n, void* stream);
 
+/* fp32 FMA issue-rate probe (the compute-roofline denominator bench.py reports beside the HBM one): n_blocks CTAs of
+ * 256 threads, each thread iters x 16 rounds of eight independent fmaf chains; out: device, n_blocks * 256 floats;
+ * *flops_out (host, optional) = the flops one launch executes.  The caller times the launch. */
+int nws_selftest_ffma_peak(float* out, int n_blocks, int iters, double* flops_out, void* stream);
+
 /* ---- stateful streaming: the same forward fed a few control frames at a time.
  * The reference only times independent, stateless forwards per buffer size (scripts/time_buffer_sizes.py:
  * 35-72); a real-time caller needs what crosses a buffer boundary carried over: the GRU state

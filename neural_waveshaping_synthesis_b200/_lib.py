@@ -96,6 +96,8 @@ def load_library():
         L.nws_stage_reverb.argtypes = [vp, vp, vp, c_int, c_int, vp, c_size_t, vp]
         L.nws_selftest_sin.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, vp]
         L.nws_selftest_sin.restype = c_int
+        L.nws_selftest_ffma_peak.argtypes = [vp, c_int, c_int, POINTER(ctypes.c_double), vp]
+        L.nws_selftest_ffma_peak.restype = c_int
         L.nws_set_pipeline.argtypes = [vp, c_int]
         L.nws_set_pipeline.restype = c_int
         L.nws_set_mlp_impl.argtypes = [vp, c_int]
@@ -146,7 +148,7 @@ EXPORTED_SYMBOLS = [
     "nws_reverb_workspace_bytes", "nws_shaper_eval_scratch_bytes", "nws_shaper_eval", "nws_launch_count",
     "nws_set_profiling", "nws_get_stage_times", "nws_selftest_umma", "nws_set_audio_impl", "nws_set_mlp_impl", "nws_stage_control_to_params", "nws_selftest_sin", "nws_set_pipeline",
     "nws_stream_create", "nws_stream_destroy", "nws_stream_reset", "nws_stream_window", "nws_stream_push",
-    "nws_loudness_workspace_bytes", "nws_extract_loudness", "nws_extract_rms",
+    "nws_loudness_workspace_bytes", "nws_extract_loudness", "nws_extract_rms", "nws_selftest_ffma_peak",
 ]
 STAGE_NAMES = ["rng", "phase_carry", "gru", "proj", "film_mlp", "noise_mlp", "noise_spectrum", "noise_filter",
                "audio_fused", "reverb"]

@@ -96,3 +96,29 @@ extern "C" int nws_selftest_sin(const float* x, float* y_acc, float* y_fast3, fl
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// fp32 FMA issue-rate probe: the denominator of the fused audio kernel's compute roofline (SURVEY.md §8(d):
+// "measure an FFMA-peak microbenchmark on the box").  Every thread runs `iters` rounds of eight independent
+// fmaf chains; flops = grid * block * iters * 8 * 2.  bench.py times it with CUDA events.
+__global__ void __launch_bounds__(256) nws_ffma_peak_kernel(float* __restrict__ out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+        x7 = x0 + 7.f;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int nws_selftest_ffma_peak(float* out, int n_blocks, int iters, double* flops_out, void* stream) {
+  if (!out || n_blocks < 1 || iters < 1) { nws_set_error("nws_selftest_ffma_peak: bad argument"); return NWS_ERR_INVALID; }
+  nws_ffma_peak_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 1e-3f);
+  NWS_LAUNCH_CHECK();
+  if (flops_out) *flops_out = (double)n_blocks * 256.0 * (double)iters * 16.0 * 8.0 * 2.0;
+  return NWS_OK;
+}

@@ -155,6 +155,7 @@ int use_abi(void* stream) {
   nws_set_audio_impl(h, 1);
   nws_selftest_umma(0, 0, 0, 8, 0, 0, stream);
   nws_selftest_sin(0, 0, 0, 0, 0, stream);
+  nws_selftest_ffma_peak(0, 1, 1, 0, stream);
   nws_stream_create(h, 1, 8, &st);
   nws_stream_reset(st, 0, 0u, 0u, stream);
   nws_stream_window(st, 2, &first, &frames);
