@@ -129,7 +129,10 @@ int check_stft_args(const char* who, int B, int N, int n_fft, int hop, int* log_
     nws_set_error("%s: n_fft = %d unsupported (powers of two from 64 to 4096)", who, n_fft);
     return NWS_ERR_UNSUPPORTED;
   }
-  if (B < 1 || hop < 1) { nws_set_error("%s: bad shape (B = %d, hop_length = %d)", who, B, hop); return NWS_ERR_INVALID; }
+  if (B < 1 || B > 65535 || hop < 1) {   // B is the grid's y dimension
+    nws_set_error("%s: bad shape (B = %d, 1..65535; hop_length = %d)", who, B, hop);
+    return NWS_ERR_INVALID;
+  }
   if (N <= n_fft / 2) {
     nws_set_error("%s: %d samples are too few for the reflect padding of n_fft = %d (need > n_fft / 2)", who, N, n_fft);
     return NWS_ERR_INVALID;
@@ -179,7 +182,7 @@ extern "C" int nws_extract_loudness(const float* audio, int B, int N, int n_fft,
 extern "C" int nws_extract_rms(const float* audio, int B, int N, int window_size, int hop_length, float* rms_out,
                                void* stream) {
   if (!audio || !rms_out) { nws_set_error("nws_extract_rms: NULL argument"); return NWS_ERR_INVALID; }
-  if (B < 1 || N < 1 || window_size < 1 || hop_length < 1) { nws_set_error("nws_extract_rms: bad shape"); return NWS_ERR_INVALID; }
+  if (B < 1 || B > 65535 || N < 1 || window_size < 1 || hop_length < 1) { nws_set_error("nws_extract_rms: bad shape"); return NWS_ERR_INVALID; }
   const int F = 1 + (N + 2 * (window_size / 2) - window_size) / hop_length;   // librosa.util.frame over the padded signal
   if (F < 1) { nws_set_error("nws_extract_rms: signal shorter than one window"); return NWS_ERR_INVALID; }
   nws_rms_kernel<<<dim3(F, B), 128, 0, (cudaStream_t)stream>>>(audio, N, window_size, hop_length, F, rms_out);
