@@ -78,3 +78,44 @@ def test_mirror_has_no_cpu_fallback():
         extract_perceptual_loudness(np.zeros(4096, np.float32))
     with pytest.raises(ValueError):
         perceptual_loudness_batch(torch.zeros(1, 4096))
+
+
+def test_adjust_controls_matches_the_notebook_cell():
+    """utils/control_adjust.py against a literal numpy/torch transcription of colab cell 15."""
+    from neural_waveshaping_synthesis_b200.utils.control_adjust import adjust_controls
+    rng = np.random.default_rng(0)
+    T = 300
+    f0 = (200 + 100 * rng.random(T)).astype(np.float32)
+    loudness = rng.random(T).astype(np.float32)
+    confidence = rng.random(T).astype(np.float32)
+    data_mean = np.array([[300.0], [0.4], [0.5]])
+    data_std = np.array([[80.0], [0.2], [0.1]])
+    for kw in (dict(), dict(octave_shift=-1, loudness_scale=1.3, loudness_floor=0.2, loudness_conf_filter=0.3,
+                            pitch_conf_filter=0.25, pitch_smoothing=4, loudness_smoothing=7)):
+        p = dict(octave_shift=1, loudness_scale=0.5, loudness_floor=0, loudness_conf_filter=0, pitch_conf_filter=0,
+                 pitch_smoothing=0, loudness_smoothing=0)
+        p.update(kw)
+        # --- the cell, verbatim in structure
+        f0_filtered = f0 * (confidence > p["pitch_conf_filter"])
+        loudness_filtered = loudness * (confidence > p["loudness_conf_filter"])
+        f0_shifted = f0_filtered * (2 ** p["octave_shift"])
+        loudness_floored = loudness_filtered * (loudness_filtered > p["loudness_floor"]) - p["loudness_floor"]
+        loudness_scaled = loudness_floored * p["loudness_scale"]
+        loud_norm = (loudness_scaled - data_mean[1]) / data_std[1]
+        f0_t = torch.tensor(f0_shifted).float()
+        loud_norm_t = torch.tensor(loud_norm).float()
+        if p["pitch_smoothing"] != 0:
+            f0_t = torch.nn.functional.conv1d(f0_t.expand(1, 1, -1), torch.ones(1, 1, p["pitch_smoothing"] * 2 + 1) /
+                                              (p["pitch_smoothing"] * 2 + 1), padding=p["pitch_smoothing"]).squeeze()
+        if p["loudness_smoothing"] != 0:
+            loud_norm_t = torch.nn.functional.conv1d(loud_norm_t.expand(1, 1, -1),
+                                                     torch.ones(1, 1, p["loudness_smoothing"] * 2 + 1) /
+                                                     (p["loudness_smoothing"] * 2 + 1), padding=p["loudness_smoothing"]).squeeze()
+        f0_norm_t = torch.tensor((f0_t.cpu() - data_mean[0]) / data_std[0]).float()
+        control = torch.stack((f0_norm_t, loud_norm_t), dim=0)
+        # ---
+        got_f0, got_control = adjust_controls(torch.from_numpy(f0), torch.from_numpy(loudness), torch.from_numpy(confidence),
+                                              data_mean, data_std, **kw)
+        assert got_control.shape == (2, T) and got_control.dtype == torch.float32
+        assert torch.allclose(got_f0, f0_t, rtol=1e-6, atol=1e-4)
+        assert torch.allclose(got_control, control, rtol=1e-5, atol=1e-5)
