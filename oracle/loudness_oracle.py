@@ -10,8 +10,12 @@ timbre-transfer use case (colab cell 14, scripts/create_dataset.py):
     extract_rms                   .../loudness_extraction.py:71-90
     linear_interpolation          neural_waveshaping_synthesis/data/utils/upsampling.py:20-36
 
-Parity status: UNPINNED.  All arithmetic of these functions lives in a third-party dependency that is
-absent from /root/reference and from this image: librosa (pinned ``librosa==0.8.0``, requirements.txt:5).
+Parity status: the reference's own code (the glue: which librosa calls, with which arguments, frame counts, the mean
+over bins, normalisation, interpolation, rms framing) is PINNED — ``oracle/gen_golden_loudness.py`` runs the real
+loudness_extraction.py / upsampling.py and ``tests/test_loudness_cpu.py`` requires this restatement to reproduce
+their outputs exactly (tests/golden/loudness_*.npz).  The layer below it is UNPINNED: all arithmetic of these functions
+lives in a third-party dependency that is absent from /root/reference and from this image: librosa (pinned
+``librosa==0.8.0``, requirements.txt:5), which the fixture generator has to replace by the restatement below.
 Its published algorithm is restated here from the 0.8.0 sources —
 
     librosa.stft              core/spectrum.py   window = scipy get_window(name, n_fft, fftbins=True);

@@ -37,6 +37,25 @@ def test_loudness_and_spectrogram_match_oracle(n, n_fft, hop):
         assert np.abs(got - ref).max() < tol, (normalise, np.abs(got - ref).max())
 
 
+@pytest.mark.parametrize("tag", ["gin", "default", "ragged"])
+def test_against_fixtures_of_the_real_reference_functions(tag):
+    """tests/golden/loudness_*.npz: outputs of the reference's own loudness_extraction.py functions
+    (oracle/gen_golden_loudness.py), every variant the file offers."""
+    import os
+    le = _mirror()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loudness_%s.npz" % tag))
+    x, n_fft, hop = z["audio"], int(z["n_fft"]), int(z["hop_length"])
+    assert np.abs(le.compute_power_spectrogram(x, n_fft, hop, "hann", 1e-5) - z["db"]).max() < 1e-3
+    assert np.abs(le.extract_perceptual_loudness(x, n_fft=n_fft, hop_length=hop, interpolate_fn=None) - z["loudness_frames"]).max() < 1.25e-5
+    assert np.abs(le.extract_perceptual_loudness(x, n_fft=n_fft, hop_length=hop, interpolate_fn=None, normalise=False)
+                  - z["loudness_frames_db"]).max() < 1e-3
+    got = le.extract_perceptual_loudness(x, n_fft=n_fft, hop_length=hop)
+    assert got.shape == z["loudness_samples"].shape and np.abs(got - z["loudness_samples"]).max() < 1.25e-5
+    assert np.abs(le.extract_rms(x, n_fft, hop, interpolate_fn=None) - z["rms_frames"]).max() < 1e-6
+    got = le.extract_rms(x, n_fft, hop)
+    assert got.shape == z["rms_samples"].shape and np.abs(got - z["rms_samples"]).max() < 1e-6
+
+
 def test_batch_rows_are_independent_and_interpolation_matches():
     le = _mirror()
     xs = np.stack([_signal(32000, seed=s) * g for s, g in ((1, 1.0), (2, 0.01), (3, 0.0))])   # loud, quiet, silent

@@ -119,3 +119,19 @@ def test_adjust_controls_matches_the_notebook_cell():
         assert got_control.shape == (2, T) and got_control.dtype == torch.float32
         assert torch.allclose(got_f0, f0_t, rtol=1e-6, atol=1e-4)
         assert torch.allclose(got_control, control, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["gin", "default", "ragged"])
+def test_oracle_glue_matches_the_real_reference_functions(tag):
+    """tests/golden/loudness_*.npz were produced by the reference's own loudness_extraction.py / upsampling.py
+    (oracle/gen_golden_loudness.py; librosa replaced by the restatement): the oracle's versions of those functions
+    must reproduce them exactly — frame counts, normalisation, interpolation, rms framing."""
+    z = np.load(os.path.join(HERE, "golden", "loudness_%s.npz" % tag))
+    x, n_fft, hop = z["audio"], int(z["n_fft"]), int(z["hop_length"])
+    assert np.array_equal(lo.compute_power_spectrogram(x, n_fft, hop, "hann", 1e-5), z["db"])
+    assert np.array_equal(lo.extract_perceptual_loudness(x, n_fft=n_fft, hop_length=hop, interpolate_fn=None), z["loudness_frames"])
+    assert np.array_equal(lo.extract_perceptual_loudness(x, n_fft=n_fft, hop_length=hop, interpolate_fn=None, normalise=False),
+                          z["loudness_frames_db"])
+    assert np.array_equal(lo.extract_perceptual_loudness(x, n_fft=n_fft, hop_length=hop), z["loudness_samples"])
+    assert np.array_equal(lo.extract_rms(x, n_fft, hop, interpolate_fn=None), z["rms_frames"])
+    assert np.array_equal(lo.extract_rms(x, n_fft, hop), z["rms_samples"])
