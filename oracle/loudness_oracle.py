@@ -29,9 +29,8 @@ Its published algorithm is restated here from the 0.8.0 sources —
     librosa.util.frame        util/utils.py      [frame_length, n_frames] strided view
 
 — and anchored on the reference's own call sites (the argument values it passes, gin/data/urmp_4second_crepe.gin:
-11-14).  ``tests/test_oracle_golden.py`` cross-checks the STFT against an independent implementation
-(torch.stft, float64) so at least the transform definition is not self-referential; no output of the real
-reference function exists to pin against.
+11-14).  ``tests/test_loudness_cpu.py`` cross-checks the STFT against an independent implementation
+(torch.stft, float64) so at least the transform definition is not self-referential.
 
 Only ``tests/`` may import this module.  The product path never does and has no CPU fallback.
 """
