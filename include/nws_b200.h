@@ -97,6 +97,17 @@ int nws_destroy(NwsHandle handle);
 /* Fills *config with the newt.gin values. */
 void nws_default_config(NwsConfig* config);
 
+/* Element count nws_load_weights reads from tensor `index` (NwsTensor order) under the newt.gin
+ * configuration, or 0 for an index out of range.  A binding compares its tensors against these before
+ * handing over raw pointers (load_state_dict's shape check, resynthesise_dataset.py:47).            */
+size_t nws_tensor_numel(int index);
+
+/* 0, or NWS_ERR_CUDA once a tensor-core kernel launched through this handle has given up waiting on
+ * an mbarrier (the wait is bounded so that a bad descriptor cannot hang the device; the kernel then writes
+ * NaNs).  Does not synchronise: every other entry point makes the same check on entry, and
+ * nws_forward_host after its own synchronise.                                                        */
+int nws_status(NwsHandle handle);
+
 /* Replaces: load_state_dict / `.to(device)` of the module parameters (resynthesise_dataset.py:47,53).
  * tensors[i] is the device pointer of tensor i in NwsTensor order (n_tensors == NWS_T_COUNT).
  * Repacks into the kernels' layouts; synchronises `stream` once (load-time only) to validate the
@@ -265,6 +276,14 @@ int nws_extract_loudness(const float* audio, int B, int N, int n_fft, int hop_le
 /* Replaces: extract_rms (loudness_extraction.py:71-90): zero-padded centred frames of window_size every
  * hop_length, sqrt(mean(x^2)).  audio [B, N] -> rms_out [B, 1 + (N + 2*(window_size/2) - window_size) / hop_length]. */
 int nws_extract_rms(const float* audio, int B, int N, int window_size, int hop_length, float* rms_out, void* stream);
+
+/* Replaces: linear_interpolation (data/utils/upsampling.py:20-36) — the default `interpolate_fn` of the two
+ * extractors above: frame values [B,F] (device, fp32) -> one float64 value per sample, np.interp over
+ * np.linspace(0, F-1, F*hop + window - hop); original_length > 0 crops to [window/2, window/2 + original_length)
+ * as the reference does, 0 keeps the padded length.  nws_interp_frames_len gives the row length of `out`.  */
+int nws_interp_frames_len(int F, int window_length, int hop_length, int original_length);
+int nws_interp_frames(const float* frames, int B, int F, int window_length, int hop_length, int original_length,
+                      double* out, void* stream);
 
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */

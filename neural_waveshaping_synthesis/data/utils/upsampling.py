@@ -1,2 +1,2 @@
 from neural_waveshaping_synthesis_b200.data.utils.upsampling import (  # noqa
-    get_padded_length, get_source_target_axes, linear_interpolation)
+    cubic_spline_interpolation, interp_frames_batch, linear_interpolation, overlap_add_upsample)

@@ -125,6 +125,14 @@ def load_library():
         L.nws_extract_loudness.restype = c_int
         L.nws_extract_rms.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp]
         L.nws_extract_rms.restype = c_int
+        L.nws_interp_frames_len.argtypes = [c_int, c_int, c_int, c_int]
+        L.nws_interp_frames_len.restype = c_int
+        L.nws_interp_frames.argtypes = [vp, c_int, c_int, c_int, c_int, c_int, vp, vp]
+        L.nws_interp_frames.restype = c_int
+        L.nws_tensor_numel.argtypes = [c_int]
+        L.nws_tensor_numel.restype = c_size_t
+        L.nws_status.argtypes = [vp]
+        L.nws_status.restype = c_int
         L.nws_shaper_eval_scratch_bytes.restype = c_size_t
         L.nws_shaper_eval.argtypes = [POINTER(vp), vp, vp, c_int, vp, vp]
         for name in ("nws_create", "nws_destroy", "nws_load_weights", "nws_build_lut", "nws_set_lut", "nws_get_lut",
@@ -149,6 +157,21 @@ EXPORTED_SYMBOLS = [
     "nws_set_profiling", "nws_get_stage_times", "nws_selftest_umma", "nws_set_audio_impl", "nws_set_mlp_impl", "nws_stage_control_to_params", "nws_selftest_sin", "nws_set_pipeline",
     "nws_stream_create", "nws_stream_destroy", "nws_stream_reset", "nws_stream_window", "nws_stream_push",
     "nws_loudness_workspace_bytes", "nws_extract_loudness", "nws_extract_rms", "nws_selftest_ffma_peak",
+    "nws_tensor_numel", "nws_status", "nws_interp_frames_len", "nws_interp_frames",
 ]
+
+# Shapes the kernels are built for (gin/models/newt.gin) in TENSOR_KEYS order.  The C side reads
+# raw pointers, so NwsEngine.load_weights refuses anything else (a model built from other gin bindings, or a
+# checkpoint with other hyper-parameters) instead of reading out of bounds.
+_MLP_SHAPES = lambda n_out: [(128, 128, 1), (128,), (128,), (128,)] * 3 + [(n_out, 128, 1), (n_out,)]
+TENSOR_SHAPES = (
+    [(384, 2), (384, 128), (384,), (384,), (128, 128, 1), (128,), (1, 101, 1), (64, 101, 1), (64,)]
+    + _MLP_SHAPES(256)
+    + [(1, 64, 1), (512, 1, 1), (512,), (512, 8, 1), (512,), (512, 8, 1), (512,), (64, 8, 1), (64,)]
+    + [(1, 64, 1), (1,)]
+    + _MLP_SHAPES(129)
+    + [(256,), (1, 31999)]
+)
+assert len(TENSOR_SHAPES) == N_TENSORS
 STAGE_NAMES = ["rng", "phase_carry", "gru", "proj", "film_mlp", "noise_mlp", "noise_spectrum", "noise_filter",
                "audio_fused", "reverb"]

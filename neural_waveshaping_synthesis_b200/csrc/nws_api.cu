@@ -55,8 +55,11 @@ extern "C" int nws_create(const NwsConfig* cfg, NwsHandle* out) {
     delete ctx;
     return NWS_ERR_CUDA;
   }
+  e = cudaHostAlloc((void**)&ctx->fault_host, sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) { *ctx->fault_host = 0; e = cudaHostGetDevicePointer((void**)&ctx->fault_dev, ctx->fault_host, 0); }
+  if (e != cudaSuccess) { nws_set_error("nws_create: %s", cudaGetErrorString(e)); nws_destroy(ctx); return NWS_ERR_CUDA; }
   int rc = nws_make_twiddle_master(ctx);
-  if (rc) { cudaFree(ctx->packed); delete ctx; return rc; }
+  if (rc) { nws_destroy(ctx); return rc; }
   // internal encoder stream + fork/join events of the pipelined forward (timing disabled: cheaper)
   {
     int prio_lo = 0, prio_hi = 0;
@@ -90,8 +93,45 @@ extern "C" int nws_destroy(NwsHandle ctx) {
   cudaFree(ctx->lut);
   cudaFree(ctx->lut2);
   cudaFree(ctx->tw_master);
+  if (ctx->fault_host) cudaFreeHost(ctx->fault_host);
   delete ctx;
   return NWS_OK;
+}
+
+extern "C" size_t nws_tensor_numel(int index) {
+  if (index < 0 || index >= NWS_T_COUNT) return 0;
+  auto mlp = [](int i, int n_out) -> size_t {   // 14 tensors of a TimeDistributedMLP (dynamic.py:20-40), depth 4
+    if (i == 12) return (size_t)n_out * kEmb;       // net.9.weight
+    if (i == 13) return (size_t)n_out;              // net.9.bias
+    return (i & 3) == 0 ? (size_t)kEmb * kEmb : (size_t)kEmb;   // net.{0,3,6}.weight | bias, LN weight, LN bias
+  };
+  if (index >= NWS_T_FILM_MLP && index < NWS_T_FILM_MLP + 14) return mlp(index - NWS_T_FILM_MLP, kFilm);
+  if (index >= NWS_T_NOISE_MLP && index < NWS_T_NOISE_MLP + 14) return mlp(index - NWS_T_NOISE_MLP, kBands);
+  switch (index) {
+    case NWS_T_GRU_W_IH: return (size_t)kGates * 2;
+    case NWS_T_GRU_W_HH: return (size_t)kGates * kEmb;
+    case NWS_T_GRU_B_IH: case NWS_T_GRU_B_HH: return kGates;
+    case NWS_T_PROJ_W: return (size_t)kEmb * kEmb;
+    case NWS_T_PROJ_B: return kEmb;
+    case NWS_T_OSC_RAND_PHASE: return kHarm;
+    case NWS_T_HMIX_W: return (size_t)kShapers * kHarm;
+    case NWS_T_HMIX_B: return kShapers;
+    case NWS_T_SHAPER_SCALE: return kShapers;
+    case NWS_T_SHAPER_W1: case NWS_T_SHAPER_B1: case NWS_T_SHAPER_B2: case NWS_T_SHAPER_B3: return (size_t)kShapers * 8;
+    case NWS_T_SHAPER_W2: case NWS_T_SHAPER_W3: return (size_t)kShapers * 64;
+    case NWS_T_SHAPER_W4: return (size_t)kShapers * 8;
+    case NWS_T_SHAPER_B4: return kShapers;
+    case NWS_T_MIX_W: return kShapers;
+    case NWS_T_MIX_B: return 1;
+    case NWS_T_NOISE_WINDOW: return kIr;
+    case NWS_T_REVERB_IR: return kReverbIr - 1;
+  }
+  return 0;
+}
+
+extern "C" int nws_status(NwsHandle ctx) {
+  if (!ctx) { nws_set_error("nws_status: NULL handle"); return NWS_ERR_INVALID; }
+  return nws_check_fault(ctx, "nws_status");
 }
 
 extern "C" int nws_load_weights(NwsHandle ctx, const float* const* tensors, int n_tensors, void* stream) {
@@ -234,8 +274,19 @@ extern "C" size_t nws_reverb_workspace_bytes(NwsHandle ctx, int B, int N) {
   return (size_t)((B + 1) / 2) * L * sizeof(float2) + 256;
 }
 
+// A tcgen05 kernel of an earlier call gave up waiting on an mbarrier (bounded waits, nws_tc.cuh) and wrote NaNs:
+// sticky until the handle is destroyed.  Read from mapped host memory — no synchronise.
+int nws_check_fault(const NwsContext* ctx, const char* who) {
+  if (ctx->fault_host && *(volatile int*)ctx->fault_host) {
+    nws_set_error("%s: a tensor-core kernel of this handle timed out on an mbarrier (results since then are invalid)", who);
+    return NWS_ERR_CUDA;
+  }
+  return NWS_OK;
+}
+
 static int check_common(NwsContext* ctx, int B, int T, void* ws, size_t ws_bytes, const char* who, NwsWorkspace* out) {
   if (!ctx) { nws_set_error("%s: NULL handle", who); return NWS_ERR_INVALID; }
+  if (int rc = nws_check_fault(ctx, who)) return rc;
   if (!ctx->weights_loaded) { nws_set_error("%s: weights not loaded", who); return NWS_ERR_STATE; }
   if (B < 1) { nws_set_error("%s: batch size must be >= 1 (got %d)", who, B); return NWS_ERR_INVALID; }
   if (T < 2) { nws_set_error("%s: T must be >= 2 control frames (got %d); the reference's STFT reflect padding has the same limit", who, T); return NWS_ERR_INVALID; }
@@ -477,7 +528,7 @@ extern "C" int nws_forward_host(NwsHandle ctx, const float* f0_host, const float
                       workspace_bytes, stream));
   NWS_CUDA_OK(cudaMemcpyAsync(out_host, d_out, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, s));
   NWS_CUDA_OK(cudaStreamSynchronize(s));
-  return NWS_OK;
+  return nws_check_fault(ctx, "nws_forward_host");   // synchronised: a timeout of this very call is visible
 }
 
 // ------------------------------------------------------------------------------------------------ stages

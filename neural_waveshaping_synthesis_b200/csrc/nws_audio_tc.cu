@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   if (wt == 0) done_s[wg] = 1;
   fill_arrive(wg, 0);   // the MMA warp is waiting for stage 0 of a tile that will not come
   }
-  if (!ok && fault) atomicExch(fault, 1);
+  if (!ok && fault) *(volatile int*)fault = 1;   // mapped host memory: a plain store, no atomic over PCIe
   nws_tc_fence_before();
   __syncthreads();
   if (tid < 32) nws_tmem_dealloc(tmem_base_s, C::kTmemColsWg * kWgs);
@@ -528,13 +528,13 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   const int grid = (int)(want < cap ? want : cap);
   const float* wu = w + ctx->lay.hmix_umma;
   const bool direct = ctx->shaper_inner_bound <= 8.0f;   // see NWS_SHAPER_SIN_INNER
-  if (use_lut && !exciter_out && ctx->lut_size == 4096) nws_audio_tc_kernel<true, false, 2><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
-  else if (use_lut && !exciter_out) nws_audio_tc_kernel<true, false, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
-  else if (use_lut) nws_audio_tc_kernel<true, true, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, nullptr);
-  else if (!exciter_out && direct) nws_audio_tc_kernel<false, false, 2><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
-  else if (!exciter_out) nws_audio_tc_kernel<false, false, 1><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
-  else if (direct) nws_audio_tc_kernel<false, true, 2><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
-  else nws_audio_tc_kernel<false, true, 1><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, nullptr);
+  if (use_lut && !exciter_out && ctx->lut_size == 4096) nws_audio_tc_kernel<true, false, 2><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, ctx->fault_dev);
+  else if (use_lut && !exciter_out) nws_audio_tc_kernel<true, false, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, ctx->fault_dev);
+  else if (use_lut) nws_audio_tc_kernel<true, true, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, ctx->fault_dev);
+  else if (!exciter_out && direct) nws_audio_tc_kernel<false, false, 2><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, ctx->fault_dev);
+  else if (!exciter_out) nws_audio_tc_kernel<false, false, 1><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, ctx->fault_dev);
+  else if (direct) nws_audio_tc_kernel<false, true, 2><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, ctx->fault_dev);
+  else nws_audio_tc_kernel<false, true, 1><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, ctx->fault_dev);
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }

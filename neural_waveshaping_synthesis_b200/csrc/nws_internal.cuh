@@ -113,6 +113,10 @@ struct NwsContext {
   float shaper_inner_bound = 1e30f;   // max_j(|b_j| + sum_i |W_ji|) over shaper layers 2-4 (set by nws_load_weights)
   int audio_impl = 1;          // 1 = tcgen05 harmonic mixer (nws_audio_tc.cu), 0 = fp32 SIMT (nws_audio.cu)
   int device = 0;
+  // mbarrier-timeout flag of the tcgen05 kernels: one int in mapped pinned host memory (the kernels write it
+  // only on a timeout; every API call reads the host side without a synchronise and fails with NWS_ERR_CUDA)
+  int* fault_host = nullptr;
+  int* fault_dev = nullptr;
   // pipelined forward: the GRU runs in time blocks on an internal stream while the main stream renders the
   // blocks already encoded
   int pipeline = 1;
@@ -153,6 +157,7 @@ int nws_reverb_exact_len(int N); // max(N, kReverbIr) when the circular convolut
 
 // ------------------------------------------------------------------ error / launch bookkeeping
 void nws_set_error(const char* fmt, ...);
+int nws_check_fault(const NwsContext* ctx, const char* who);
 extern thread_local uint64_t g_nws_launches;
 
 // cudaFuncSetAttribute is per device: "first use" flags are kept per device ordinal (a process may drive

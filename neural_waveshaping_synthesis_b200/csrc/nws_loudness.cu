@@ -189,3 +189,55 @@ extern "C" int nws_extract_rms(const float* audio, int B, int N, int window_size
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Frame rate -> sample rate, linear (data/utils/upsampling.py:20-36: np.interp of the frame values over
+// np.linspace(0, F-1, P), P = F*hop + window - hop, then [window/2 : window/2 + original_length]).  float64 like numpy:
+// target x_i = i * step (step = (F-1)/(P-1); the last point is exactly F-1), j = floor(x), slope_j = y[j+1] - y[j]
+// (the source axis is the integers, so the division by x[j+1] - x[j] is by 1), out = slope_j * (x - j) + y[j] with
+// separate roundings.  One thread per output sample.
+__global__ void nws_interp_frames_kernel(const float* __restrict__ frames, int F, long long P, int skip, int out_len,
+                                         double* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= out_len) return;
+  const long long i = o + skip;
+  const float* y = frames + (size_t)b * F;
+  double r;
+  if (F == 1) {
+    r = (double)y[0];
+  } else {
+    const double step = (double)(F - 1) / (double)(P - 1);
+    const double x = i == P - 1 ? (double)(F - 1) : __dmul_rn((double)i, step);
+    int j = (int)x;
+    if (j >= F - 1) {
+      r = (double)y[F - 1];
+    } else {
+      const double y0 = (double)y[j], slope = __dsub_rn((double)y[j + 1], y0);
+      r = x == (double)j ? y0 : __dadd_rn(__dmul_rn(slope, __dsub_rn(x, (double)j)), y0);
+    }
+  }
+  out[(size_t)b * out_len + o] = r;
+}
+
+extern "C" int nws_interp_frames_len(int F, int window_length, int hop_length, int original_length) {
+  if (F < 1 || window_length < 1 || hop_length < 1 || original_length < 0) return 0;
+  const long long P = (long long)F * hop_length + window_length - hop_length;
+  if (P < 1 || P > 0x7fffffffLL) return 0;
+  if (!original_length) return (int)P;
+  const long long rest = P - window_length / 2;
+  return (int)(rest < 0 ? 0 : (rest < original_length ? rest : original_length));
+}
+
+extern "C" int nws_interp_frames(const float* frames, int B, int F, int window_length, int hop_length,
+                                 int original_length, double* out, void* stream) {
+  if (!frames || !out) { nws_set_error("nws_interp_frames: NULL argument"); return NWS_ERR_INVALID; }
+  if (B < 1 || B > 65535) { nws_set_error("nws_interp_frames: bad batch size %d", B); return NWS_ERR_INVALID; }
+  const int out_len = nws_interp_frames_len(F, window_length, hop_length, original_length);
+  if (out_len < 1) { nws_set_error("nws_interp_frames: bad shape (F %d, window %d, hop %d, original_length %d)", F, window_length, hop_length, original_length); return NWS_ERR_INVALID; }
+  const long long P = (long long)F * hop_length + window_length - hop_length;
+  const int skip = original_length ? window_length / 2 : 0;
+  nws_interp_frames_kernel<<<dim3((out_len + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(frames, F, P, skip, out_len, out);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
   }
   nws_tc_fence_before();
   __syncthreads();
-  if (fault_s && fault && tid == 0) atomicExch(fault, 1);
+  if (fault_s && fault && tid == 0) *(volatile int*)fault = 1;
   if (warp == 0) nws_tmem_dealloc(tmem, 512);
 }
 
@@ -427,7 +427,7 @@ int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, flo
   const int rounds_split2 = (2 * tiles + grid_split - 1) / grid_split;
   p.split = rounds_split2 < rounds_whole2 ? 1 : 0;
   const int grid = p.split ? grid_split : grid_whole;
-  nws_mlp_tc_kernel<<<grid, kMlpThreads, smem, s>>>(p, nullptr);
+  nws_mlp_tc_kernel<<<grid, kMlpThreads, smem, s>>>(p, ctx->fault_dev);
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }

@@ -85,7 +85,17 @@ class NwsEngine:
         missing = [k for k in _lib.TENSOR_KEYS if k not in state]
         if missing:
             raise KeyError("missing weights: %s" % missing)
+        bad = ["%s: %s, built for %s" % (k, tuple(state[k].shape), shp)
+               for k, shp in zip(_lib.TENSOR_KEYS, _lib.TENSOR_SHAPES) if tuple(state[k].shape) != shp]
+        if bad:
+            raise NotImplementedError("the CUDA path is built for the gin/models/newt.gin sizes only; these tensors "
+                                      "have other shapes (the reference would run them, this library reads raw "
+                                      "pointers and refuses): " + "; ".join(bad))
         tensors = [_as_f32(state[k], self.device) for k in _lib.TENSOR_KEYS]
+        for i, t in enumerate(tensors):   # belt and braces: the library's own element counts
+            if t.numel() != self.lib.nws_tensor_numel(i):
+                raise NotImplementedError("tensor %s has %d elements, the library reads %d" %
+                                          (_lib.TENSOR_KEYS[i], t.numel(), self.lib.nws_tensor_numel(i)))
         arr = (ctypes.c_void_p * _lib.N_TENSORS)(*[t.data_ptr() for t in tensors])
         with torch.cuda.device(self.device):
             _lib.check(self.lib.nws_load_weights(self.handle, arr, _lib.N_TENSORS, self._stream()))

@@ -2,16 +2,20 @@
 NeuralWaveshaping instance that owns them (weights are loaded into the C handle as one set)."""
 import weakref
 
+# sub-module -> weak reference to its root.  Kept outside the modules' __dict__: a weak reference is a per-process
+# cache, and inside the module it would make torch.save(model) / pickle fail.
+_ROOTS = weakref.WeakKeyDictionary()
+
 
 class BoundToRoot:
-    """Mixin: `self._nws_root` is a weak reference to the owning NeuralWaveshaping."""
-    _nws_root_ref = None
+    """Mixin: the owning NeuralWaveshaping is looked up through a weak side table."""
 
     def _bind_root(self, root):
-        object.__setattr__(self, "_nws_root_ref", weakref.ref(root))
+        _ROOTS[self] = weakref.ref(root)
 
     def _root(self):
-        root = self._nws_root_ref() if self._nws_root_ref is not None else None
+        ref = _ROOTS.get(self)
+        root = ref() if ref is not None else None
         if root is None:
             raise NotImplementedError(
                 "%s.forward runs as a CUDA stage of a NeuralWaveshaping model; construct it through "

@@ -61,6 +61,15 @@ class _PermissivePickle:
         return _PermissiveUnpickler(f, **kw).load()
 
 
+def _version_of(t: torch.Tensor) -> int:
+    """In-place modification counter of a tensor; tensors created under torch.inference_mode() do not track one
+    (reading it raises): fall back to the pointer alone for those."""
+    try:
+        return t._version
+    except Exception:
+        return -1
+
+
 @gin.configurable
 class NeuralWaveshaping(nn.Module):
     def __init__(self, n_waveshapers: int, control_hop: int, sample_rate: float = 16000,
@@ -92,6 +101,33 @@ class NeuralWaveshaping(nn.Module):
         if control_hop != 128 or n_waveshapers != 64 or int(sample_rate) != 16000:
             raise NotImplementedError("the CUDA path is built for gin/models/newt.gin "
                                       "(control_hop 128, 64 waveshapers, 16 kHz)")
+
+    # ------------------------------------------------------------------ copies / pickles
+    # The engines own ctypes handles (one C context per device): they are per-instance caches, never state.  A copy
+    # or an unpickled model starts without them and builds its own on its first forward — sharing a handle between
+    # two modules would free it twice.
+    _TRANSIENT = ("_engines", "_loaded", "_wt_cache")
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._TRANSIENT:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        object.__setattr__(self, "_engines", {})
+        object.__setattr__(self, "_loaded", {})
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__setstate__({k: copy.deepcopy(v, memo) for k, v in self.__getstate__().items()})
+        for m in new.modules():
+            if isinstance(m, BoundToRoot):
+                m._bind_root(new)
+        return new
 
     # ------------------------------------------------------------------ engine management
     def _mlp_index(self, module) -> int:
@@ -138,7 +174,7 @@ class NeuralWaveshaping(nn.Module):
         if tensors[0].device != dev:   # the module was moved since the tensor list was cached
             object.__setattr__(self, "_wt_cache", None)
             sd, tensors = self._weight_tensors()
-        sig = tuple([(t.data_ptr(), t._version) for t in tensors])
+        sig = tuple([(t.data_ptr(), _version_of(t)) for t in tensors])
         tag = self._loaded.get(dev)
         if tag is None or tag[0] != sig:
             for m in self.modules():
@@ -148,7 +184,7 @@ class NeuralWaveshaping(nn.Module):
             tag = (sig, None)
         if isinstance(self.newt, FastNEWT):
             t = self.newt.lookup_table
-            lsig = (t.data_ptr(), t._version, self.newt.table_min, self.newt.table_max)
+            lsig = (t.data_ptr(), _version_of(t), self.newt.table_min, self.newt.table_max)
             if tag[1] != lsig:
                 eng.set_lut(t, self.newt.table_min, self.newt.table_max)
                 tag = (tag[0], lsig)

@@ -40,6 +40,20 @@ def test_tensor_order_matches_header():
     assert all(k in z.files for k in _lib.TENSOR_KEYS)
 
 
+def test_tensor_numel_matches_shape_table(libpath):
+    """The library's own element counts (nws_tensor_numel) agree with the binding's shape table and with the
+    shipped checkpoints, so NwsEngine.load_weights can refuse other configurations before any raw pointer is read."""
+    from neural_waveshaping_synthesis_b200 import _lib
+    lib = ctypes.CDLL(libpath)
+    lib.nws_tensor_numel.restype = ctypes.c_size_t
+    lib.nws_tensor_numel.argtypes = [ctypes.c_int]
+    z = np.load(os.path.join(REPO, "tests", "golden", "weights_vn.npz"))
+    for i, (k, shp) in enumerate(zip(_lib.TENSOR_KEYS, _lib.TENSOR_SHAPES)):
+        assert tuple(z[k].shape) == shp, k
+        assert lib.nws_tensor_numel(i) == int(np.prod(shp)), k
+    assert lib.nws_tensor_numel(-1) == 0 and lib.nws_tensor_numel(_lib.N_TENSORS) == 0
+
+
 def _model():
     import gin
     from neural_waveshaping_synthesis.models.neural_waveshaping import NeuralWaveshaping
@@ -165,6 +179,9 @@ int use_abi(void* stream) {
   nws_extract_rms(0, 1, 4096, 2048, 512, 0, stream);
   (void)nws_shaper_eval_scratch_bytes();
   (void)nws_launch_count(1);
+  (void)nws_tensor_numel(NWS_T_REVERB_IR);
+  (void)nws_status(h);
+  nws_interp_frames(0, 1, 4, 1024, 128, nws_interp_frames_len(4, 1024, 128, 0), 0, stream);
   return nws_destroy(h);
 }
 """)
@@ -175,3 +192,43 @@ int use_abi(void* stream) {
     declared = set(re.findall(r"\b(nws_[a-z_0-9]+)\s*\(", header))
     used = set(re.findall(r"\b(nws_[a-z_0-9]+)\s*\(", src.read_text()))
     assert declared <= used, sorted(declared - used)
+
+
+def test_model_copies_and_pickles_without_its_engines():
+    """The per-device engines hold ctypes handles: they are caches, not state.  deepcopy / torch.save of a model
+    that has already run must work and must not share a handle (both used to raise)."""
+    import copy
+    import io
+    NW = _model()
+    m = NW().eval()
+    for sub in m.modules():
+        if hasattr(sub, "_bind_root"):
+            sub._bind_root(m)
+    m._engines["cuda:0"] = ctypes.pointer(ctypes.c_int(5))    # what a first forward leaves behind (unpicklable)
+    m._loaded["cuda:0"] = ("sig", None)
+    m2 = copy.deepcopy(m)
+    assert m2._engines == {} and m2._loaded == {} and m2.embedding._root() is m2 and m.embedding._root() is m
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m3 = torch.load(buf, weights_only=False)
+    assert m3._engines == {} and all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m3.state_dict().values()))
+    with torch.inference_mode():
+        m4 = NW()
+    from neural_waveshaping_synthesis_b200.models.neural_waveshaping import _version_of
+    assert all(isinstance(_version_of(t), int) for t in m4.state_dict().values())
+
+
+def test_ref_script_fixtures_are_verbatim():
+    """tests/golden/ref_scripts/*.py.txt are byte copies of the reference's scripts (what tests/test_gpu_ref_scripts.py
+    executes on the GPU box, where /root/reference does not exist)."""
+    import hashlib
+    d = os.path.join(REPO, "tests", "golden", "ref_scripts")
+    sums = dict(reversed(line.split()) for line in open(os.path.join(d, "SHA256SUMS")) if line.strip())
+    assert len(sums) == 3
+    for name, digest in sums.items():
+        blob = open(os.path.join(d, name), "rb").read()
+        assert hashlib.sha256(blob).hexdigest() == digest, name
+        ref = os.path.join("/root/reference/scripts", name[:-len(".txt")])
+        if os.path.exists(ref):
+            assert open(ref, "rb").read() == blob, name

@@ -1,6 +1,8 @@
 """GPU parity of the control-side loudness extractors (csrc/nws_loudness.cu, through the C ABI and the host mirror
 of data/utils/loudness_extraction.py) against the numpy oracle (oracle/loudness_oracle.py: librosa 0.8.0 restated).
 Stated tolerances: dB spectrogram 1e-3 dB, per-frame loudness 1e-3 dB = 1.25e-5 normalised, rms 1e-6 relative."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -93,3 +95,21 @@ def test_loudness_errors():
         le.perceptual_loudness_batch(torch.zeros(1, 4096), 1024, 128)    # CPU tensor: no fallback
     with pytest.raises(NotImplementedError):
         le.extract_perceptual_loudness(np.zeros(4096, np.float32), window="hamming")
+
+
+def test_linear_interpolation_on_device_matches_reference_fixture():
+    """upsampling.linear_interpolation (nws_interp_frames: np.interp's float64 arithmetic, one thread per sample)
+    against vectors made by the reference's own upsampling.py — including F = 1 and the un-cropped form."""
+    from neural_waveshaping_synthesis.data.utils import upsampling as up
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "upsampling.npz"))
+    for i, (F, window, hop, orig) in enumerate(z["cases"]):
+        frames = z["frames_%d" % i]
+        ref = z["linear_%d" % i]
+        got = up.linear_interpolation(frames, int(window), int(hop), original_length=int(orig) or None)
+        assert got.dtype == np.float64 and got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-12 * max(1.0, float(np.abs(ref).max())), i
+    # batched, device in / device out
+    fr = torch.from_numpy(np.stack([z["frames_0"], z["frames_0"][::-1].copy()])).cuda()
+    out = up.interp_frames_batch(fr, 2048, 512, 24000)
+    assert out.shape == (2, 24000) and out.is_cuda
+    assert np.abs(out[0].cpu().numpy() - z["linear_0"]).max() <= 1e-11

@@ -312,6 +312,63 @@ def test_full_size_batch_properties():
     assert e[0] < TOL_CKPT_MAX and e[1] < TOL_CKPT_RMS, e
 
 
+@pytest.mark.parametrize("tag", ["vn", "randinit"])
+def test_full_size_newt_batch_vs_oracle(tag):
+    """BASELINE configs[2] (C3): the full NEWT sine-MLP shapers at B = 64 x 4 s — two rows against the oracle,
+    repeat runs bit-identical.  (The FastNEWT variant of the same size is test_full_size_batch_properties.)"""
+    m, w = _model(tag, False)
+    gen = torch.Generator().manual_seed(21)
+    if tag == "vn":
+        f0, control = oracle.realistic_inputs(500, w["data_mean"].numpy(), w["data_std"].numpy(), B=1)
+        f0b = (f0 * (0.3 + 1.4 * torch.rand(64, 1, 1, generator=gen))).contiguous()
+        cb = (control + 0.1 * torch.randn(64, 2, 1, generator=gen)).contiguous()
+    else:   # the timing scripts' inputs (time_forward_pass.py:27-40)
+        f0b, cb = torch.rand(64, 1, 500, generator=gen), torch.rand(64, 2, 500, generator=gen)
+    u, noise = oracle.draw_rng(500, 13)
+    args = dict(phase_shift=u.reshape(-1).cuda(), noise=noise.cuda())
+    with torch.no_grad():
+        y1 = m(f0b.cuda(), cb.cuda(), **args)
+        y2 = m(f0b.cuda(), cb.cuda(), **args)
+    assert y1.shape == (64, 64000) and torch.isfinite(y1).all() and torch.equal(y1, y2)
+    tmax, trms = _tols(tag)
+    for row in (5, 62):
+        ref = oracle.forward(w, f0b[row:row + 1], cb[row:row + 1], u, noise)
+        e = err(y1[row:row + 1], ref)
+        assert e[0] < tmax and e[1] < trms, (tag, row, e)
+
+
+def test_model_copy_after_forward_and_foreign_shapes():
+    """(1) deepcopy / torch.save of a model that has run (its engines hold ctypes handles) work and the copy
+    renders the same audio through its own handle; (2) a model built with other hyper-parameters than newt.gin's is
+    refused with NotImplementedError before any raw pointer reaches the library."""
+    import copy
+    import io
+    m, w = _model("randinit", True)
+    c = load_case("small_randinit_fast")
+    args = dict(phase_shift=c["u_phase"].cuda(), noise=c["noise"].cuda())
+    with torch.no_grad():
+        y = m(c["f0"].cuda(), c["control"].cuda(), **args)
+        m2 = copy.deepcopy(m)
+        assert m2._engines == {}
+        y2 = m2(c["f0"].cuda(), c["control"].cuda(), **args)
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        buf.seek(0)
+        y3 = torch.load(buf, weights_only=False)(c["f0"].cuda(), c["control"].cuda(), **args)
+    assert torch.equal(y, y2) and torch.equal(y, y3)
+    assert m2._engines and m._engines and next(iter(m2._engines.values())) is not next(iter(m._engines.values()))
+    import gin
+    from neural_waveshaping_synthesis.models.neural_waveshaping import NeuralWaveshaping
+    for binding in ("Reverb.length_in_seconds = 1", "HarmonicOscillator.n_harmonics = 60", "NEWT.shaping_fn_size = 16"):
+        gin.clear_config()
+        gin.parse_config_file(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gin", "models", "newt.gin"))
+        gin.parse_config(binding)
+        other = NeuralWaveshaping().eval().to("cuda:0")
+        with pytest.raises(NotImplementedError, match="newt.gin"):
+            other(c["f0"].cuda(), c["control"].cuda())
+    gin.clear_config()
+
+
 def test_c5_shard_of_256_utterances():
     """BASELINE configs[4]: 2048 utterances over 8 GPUs = 256 x 4 s per GPU.  More utterances than SMs: the GRU runs
     in two waves and the forward takes the serial (non-pipelined) order — rows must equal the same utterances

@@ -135,3 +135,21 @@ def test_oracle_glue_matches_the_real_reference_functions(tag):
     assert np.array_equal(lo.extract_perceptual_loudness(x, n_fft=n_fft, hop_length=hop), z["loudness_samples"])
     assert np.array_equal(lo.extract_rms(x, n_fft, hop, interpolate_fn=None), z["rms_frames"])
     assert np.array_equal(lo.extract_rms(x, n_fft, hop), z["rms_samples"])
+
+
+def test_upsampling_host_interpolators_match_reference_fixture():
+    """cubic_spline_interpolation / overlap_add_upsample (host numpy/scipy by the interface's definition) and the
+    oracle's linear_interpolation against vectors made by the reference's own upsampling.py
+    (oracle/gen_golden_upsampling.py)."""
+    from neural_waveshaping_synthesis.data.utils import upsampling as up
+    z = np.load(os.path.join(HERE, "golden", "upsampling.npz"))
+    for i, (F, window, hop, orig) in enumerate(z["cases"]):
+        frames = z["frames_%d" % i]
+        kw = dict(window_length=int(window), hop_length=int(hop), original_length=int(orig) or None)
+        assert np.array_equal(lo.linear_interpolation(frames, **kw), z["linear_%d" % i])
+        if "cubic_%d" % i in z.files:
+            got = up.cubic_spline_interpolation(frames, **kw)
+            assert got.shape == z["cubic_%d" % i].shape and np.abs(got - z["cubic_%d" % i]).max() < 1e-10
+        if "ola_%d" % i in z.files:
+            got = up.overlap_add_upsample(frames, **kw)
+            assert got.shape == z["ola_%d" % i].shape and np.abs(got - z["ola_%d" % i]).max() < 1e-12
