@@ -11,6 +11,12 @@ torch.rand like scripts/time_forward_pass.py:27-40, random-init weights of newt.
 scaling), one process per GPU under torchrun, no collective on the data path, one NCCL
 all-reduce/all-gather of (seconds, samples) at the end.
 
+The same line carries a `configs` object with the other BASELINE.json configurations, each with its own parity figure
+against tests/golden: `c3` (configs[2]: full NEWT shapers, 64 x 4 s, own roofline), `c4` (configs[3]: B = 1 stateless
+forward and stateful SynthStream.push at the buffer sizes of scripts/time_buffer_sizes.py:13, next to the CPU port at
+the same sizes) and `c5` (configs[4]: a GLOBAL batch of 2048 utterances split over the ranks with shard_bounds —
+256 per GPU at N = 8 — forward plus a timed NCCL gather of the audio).  `value` stays configs[1] so the series is comparable.
+
 One JSON line on stdout (rank 0).  `value` is device-timed (CUDA events around each step on the
 launch stream, inputs resident in HBM, L2 flushed between steps); `e2e` is the same forward through
 the public module API from pinned host tensors with the H2D/D2H copies inside the timed region;
@@ -49,6 +55,8 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--cpu-batch", type=int, default=8, help="utterances per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs.c3/c4/c5 legs (quick runs)")
+    ap.add_argument("--c5-global-batch", type=int, default=2048)
     ap.add_argument("--inputs", default="rand", choices=["rand", "realistic"],
                     help="rand = the reference timing scripts' torch.rand f0/control (the contract's workload); "
                          "realistic = violin checkpoint + vibrato around 110-660 Hz (SURVEY.md 8(d)'s second input set)")
@@ -60,18 +68,51 @@ def env_rank():
 
 
 class ClockSampler:
-    """nvidia-smi sampling of SM clock and throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed regions: NVML polled from a thread every ~2 ms (a 20-step run is
+    only ~100 ms long: `nvidia-smi -lms 20` gave 7 samples), falling back to an nvidia-smi loop if NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread, self.stop_flag, self.source = index, [], None, None, False, None
+
+    def _nvml_loop(self, pynvml, h):
+        # NVML clocks-event-reason bits (nvml.h): HwSlowdown 0x8, HwThermalSlowdown 0x40, SwThermalSlowdown 0x20, SwPowerCap 0x4
+        bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = get_reasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.source = "nvml, 2 ms period"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(pynvml, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 20"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -81,22 +122,25 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
                 continue
-            for n, v in zip(names, r[2:6]):
+            for n, v in zip(self.NAMES, r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def build_weights():
@@ -186,10 +230,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def profile_path(variant):
+    """The committed `ncu --set full` summary of the dominant kernel for this variant: newest round first."""
+    tag = "lut" if variant == "fastnewt" else "mlp"
+    for rnd in ("r2", "r1"):
+        path = os.path.join(REPO, "profiles", "%s_ncu_audio_tc_%s.json" % (rnd, tag))
+        if os.path.exists(path):
+            return path
+    return os.path.join(REPO, "profiles", "r1_ncu_audio_tc_%s.json" % tag)
+
+
 def ncu_traffic(variant):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
     `ncu --set full` capture of this workload (profiles/, written by scripts/ncu_summary.py); None if absent."""
-    path = os.path.join(REPO, "profiles", "r1_ncu_audio_tc_%s.json" % ("lut" if variant == "fastnewt" else "mlp"))
+    path = profile_path(variant)
     try:
         d = json.load(open(path))[0]
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -204,11 +258,12 @@ def issue_view(variant, kernel_ms=None, clocks=None, ffma_tflops=None):
     Instruction counts and pipe activity from the committed ncu capture of this workload (profiles/); the kernel
     time, the SM clock and the fp32 FMA rate are measured live, so `frac_of_issue_peak` = warp-instructions per
     second ÷ (SMs x 4 schedulers x SM clock) is this run's fraction of the issue roofline."""
-    path = os.path.join(REPO, "profiles", "r1_ncu_audio_tc_%s.json" % ("lut" if variant == "fastnewt" else "mlp"))
+    path = profile_path(variant)
     try:
         d = json.load(open(path))[0]
         g = lambda k: d[k]["value"]
         v = {"bound": "warp-instruction issue (fp32 SIMT epilogue + sine generation)",
+             "counts_from": "committed ncu capture (not measured in this run): profiles/" + os.path.basename(path),
              "issue_slot_utilisation": g("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
              "tensor_pipe_active": g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active") / 100.0,
              "warp_instructions_per_launch": g("smsp__inst_executed.sum"), "source": os.path.basename(path)}
@@ -223,6 +278,241 @@ def issue_view(variant, kernel_ms=None, clocks=None, ffma_tflops=None):
         return v
     except Exception:
         return {"bound": "warp-instruction issue", "source": None}
+
+
+BUFFER_SIZES = [256, 512, 1024, 2048, 4096, 8192, 16384, 32768]   # scripts/time_buffer_sizes.py:13
+STREAM_SIZES = [256, 512, 1024, 2048, 4096]                       # BASELINE.json configs[3]'s range
+
+
+def golden_case(name, prefix=""):
+    """A fixture of tests/golden (made by the real reference, oracle/gen_golden.py) as torch tensors; the noise vector is
+    regenerated with the reference's draw order (torch CPU generator: rand(1,101,1), then rand(128T-1)) and the stored
+    phase draw guards against RNG drift.  numpy + torch only: the GPU arm never imports oracle/."""
+    import numpy as np
+    import torch
+    z = np.load(os.path.join(REPO, "tests", "golden", name + ".npz"))
+    c = {k[len(prefix):]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith(prefix)}
+    T = c["f0"].shape[-1]
+    torch.manual_seed(int(c["rng_seed"]))
+    u = torch.rand(1, 101, 1)
+    c["noise"] = torch.rand(HOP * T - 1)
+    if not torch.equal(u.reshape(-1), c["u_phase"]):
+        raise RuntimeError("torch CPU RNG stream changed: golden noise cannot be regenerated")
+    return c
+
+
+def parity_max_abs(model, case, dev, out_key="out"):
+    import torch
+    with torch.no_grad():
+        y = model(case["f0"].to(dev), case["control"].to(dev), phase_shift=case["u_phase"].to(dev), noise=case["noise"].to(dev))
+    return float((y.cpu().double() - case[out_key].double()).abs().max())
+
+
+def pctl(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(q * len(xs)))]
+
+
+def config_c3(args, cpu_model, dev, timed_steps, flush, peaks_hbm, clocks_now):
+    """BASELINE.json configs[2]: full NEWT sine-MLP shapers, batch 64 x 4 s, one GPU."""
+    import copy
+    import torch
+    model = copy.deepcopy(cpu_model).to(dev)
+    B, T = args.batch_per_gpu, int(SR * args.seconds) // HOP
+    N = T * HOP
+    torch.manual_seed(101)
+    f0, control = torch.rand(B, 1, T, device=dev), torch.rand(B, 2, T, device=dev)
+    k = max(5, min(args.steps, 30))
+    with torch.no_grad():
+        for _ in range(3):
+            model(f0, control)
+        per = timed_steps(k, lambda: model(f0, control))
+        eng = model._engine_for(f0)
+        eng.set_profiling(True)
+        acc = {}
+        for _ in range(5):
+            flush.fill_(1)
+            model(f0, control)
+            for kk, v in eng.stage_times_ms().items():
+                acc[kk] = acc.get(kk, 0.0) + v / 5
+        eng.set_profiling(False)
+    ms = sum(per) / len(per)
+    audio_ms = acc.get("audio_fused", 0.0)
+    algo = B * T * ALGO_BYTES_PER_UTT_FRAME
+    achieved = algo / (audio_ms * 1e-3) / 1e9 if audio_ms > 0 else None
+    # arithmetic view: 1,701 sines per sample go through the SFU (16 lanes / SM / clock): the pipe that bounds this kernel
+    sfu = None
+    if audio_ms > 0 and clocks_now and clocks_now.get("sm_mhz"):
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        sfu_peak = n_sm * 16 * clocks_now["sm_mhz"] * 1e6
+        sfu = {"sines_per_sample": 1701, "mufu_per_s": B * N * 1701 / (audio_ms * 1e-3), "mufu_peak_per_s": sfu_peak,
+               "frac_of_sfu_peak": B * N * 1701 / (audio_ms * 1e-3) / sfu_peak}
+    return {
+        "workload": "NEWT MLP forward, batch %d x %g s @ 16 kHz (BASELINE.json configs[2])" % (B, args.seconds),
+        "ms_per_step": ms, "ms_per_step_p90": pctl(per, 0.9), "steps": k, "value": B * N / (ms * 1e-3), "unit": "samples/s",
+        "rtf_per_utterance": (ms * 1e-3) / (B * args.seconds),
+        "parity_max_abs_vs_golden": {"kat_randinit_newt": parity_max_abs(model, golden_case("kat_randinit_newt"), dev)},
+        "roofline": {"kernel": "nws_audio_tc_kernel<MLP>", "bound": "hbm", "achieved": achieved, "peak": peaks_hbm, "unit": "GB/s",
+                     "frac": (achieved / peaks_hbm) if achieved else None, "traffic": ncu_traffic("newt"),
+                     "algorithmic_bytes_per_launch": algo, "kernel_ms": audio_ms,
+                     "kernel_share_of_step": audio_ms / sum(acc.values()) if acc else None,
+                     "issue_view": issue_view("newt", audio_ms, clocks_now), "sfu_view": sfu},
+        "stages_ms": acc, "stages_order": "serial (stage profiling disables the pipelined order)",
+    }
+
+
+def config_c4(args, cpu_model, dev, flush):
+    """BASELINE.json configs[3]: B = 1 at the buffer sizes of scripts/time_buffer_sizes.py — (a) the reference script's
+    stateless forward (nothing carried between buffers, time_buffer_sizes.py:66-72), cold (L2 flushed before each
+    call) and warm; (b) the stateful SynthStream.push of the same number of samples; (c) the CPU port beside them."""
+    import copy
+    import torch
+    from neural_waveshaping_synthesis.models.modules.shaping import FastNEWT
+    out = {"workload": "B = 1 buffer sweep (BASELINE.json configs[3]; scripts/time_buffer_sizes.py:13,66-75)",
+           "timing": "CUDA events per call on the launch stream; `cold` = 256 MiB L2 flush before every call, `warm` = back to back",
+           "sizes": BUFFER_SIZES, "stream_sizes": STREAM_SIZES}
+    iters = 40
+    sweep = golden_case  # noqa: F841
+    for variant in ("fastnewt", "newt"):
+        model = copy.deepcopy(cpu_model)
+        if variant == "fastnewt":
+            model.newt = FastNEWT(model.newt)
+        model = model.to(dev)
+        rows = {}
+        with torch.no_grad():
+            for bs in BUFFER_SIZES:
+                T = bs // HOP
+                torch.manual_seed(bs)
+                f0, control = torch.rand(1, 1, T, device=dev), torch.rand(1, 2, T, device=dev)
+                for _ in range(5):
+                    model(f0, control)
+                torch.cuda.synchronize(dev)
+
+                def run(with_flush):
+                    evs = []
+                    for _ in range(iters):
+                        if with_flush:
+                            flush.fill_(1)
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        model(f0, control)
+                        b.record()
+                        evs.append((a, b))
+                    torch.cuda.synchronize(dev)
+                    return [a.elapsed_time(b) for a, b in evs]
+
+                cold, warm = run(True), run(False)
+                rows[str(bs)] = {"ms_median_cold": statistics.median(cold), "ms_p90_cold": pctl(cold, 0.9),
+                                 "ms_median_warm": statistics.median(warm), "ms_p90_warm": pctl(warm, 0.9),
+                                 "rtf_warm": statistics.median(warm) * 1e-3 / (bs / SR)}
+            # stateful streaming: pushes of bs samples (bs / 128 frames) into one running stream
+            stream_rows = {}
+            for bs in STREAM_SIZES:
+                n = bs // HOP
+                st = model.stream(batch_size=1, max_frames=max(n, 2))
+                st.reset()
+                torch.manual_seed(bs)
+                f0, control = torch.rand(1, 1, n, device=dev) * 200 + 100, torch.rand(1, 2, n, device=dev)
+                for _ in range(5):
+                    st.push(f0, control)
+                torch.cuda.synchronize(dev)
+                evs = []
+                for _ in range(iters):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    st.push(f0, control)
+                    b.record()
+                    evs.append((a, b))
+                torch.cuda.synchronize(dev)
+                ts = [a.elapsed_time(b) for a, b in evs]
+                stream_rows[str(bs)] = {"ms_median": statistics.median(ts), "ms_p90": pctl(ts, 0.9),
+                                        "rtf": statistics.median(ts) * 1e-3 / (bs / SR)}
+                del st
+        par = {}
+        for bs in (256, 4096, 32768):
+            c = golden_case("sweep_randinit", "bs%d_" % bs)
+            par["bs%d" % bs] = parity_max_abs(model, c, dev, "out_fast" if variant == "fastnewt" else "out")
+        out[variant] = {"stateless_forward": rows, "stream_push": stream_rows, "parity_max_abs_vs_golden": par}
+    return out
+
+
+def config_c4_cpu(cpu_model, threads=8):
+    """The CPU port at the same buffer sizes (rank 0, N = 1 only; a bounded sample: 3 calls per size after one warm-up)."""
+    import torch
+    from oracle import nws_oracle as oracle
+    torch.set_num_threads(min(threads, os.cpu_count() or 1))
+    w = {k: v.detach().cpu().clone() for k, v in cpu_model.state_dict().items()}
+    lut = oracle.build_lookup_table(w)
+    out = {"kind": "port", "cores": torch.get_num_threads(), "sample": "3 calls per size after 1 warm-up, B = 1, oracle port"}
+    for variant, table in (("fastnewt", lut), ("newt", None)):
+        rows = {}
+        for bs in BUFFER_SIZES:
+            T = bs // HOP
+            torch.manual_seed(bs)
+            f0, control = torch.rand(1, 1, T), torch.rand(1, 2, T)
+            ts = []
+            for i in range(4):
+                t0 = time.perf_counter()
+                u, noise = oracle.draw_rng(T)
+                oracle.forward(w, f0, control, u, noise, lut=table, faithful_loop=True)
+                if i:
+                    ts.append((time.perf_counter() - t0) * 1e3)
+            rows[str(bs)] = {"ms_median": statistics.median(ts), "rtf": statistics.median(ts) * 1e-3 / (bs / SR)}
+        out[variant] = rows
+    return out
+
+
+def config_c5(args, model, dev, rank, world, dist):
+    """BASELINE.json configs[4]: one GLOBAL batch of 2048 utterances x 4 s, split over the ranks in contiguous slices
+    (sharding.shard_bounds: 256 per GPU at N = 8), forward on every rank, then the audio gathered on every rank over
+    NCCL (sharding.gather_audio) — strong scaling of a fixed job.  Time = max over ranks of (forward + gather)."""
+    import torch
+    from neural_waveshaping_synthesis_b200.sharding import aggregate_throughput, gather_audio, shard_bounds
+    G, T = args.c5_global_batch, int(SR * args.seconds) // HOP
+    N = T * HOP
+    lo, hi = shard_bounds(G, rank, world)
+    gen = torch.Generator().manual_seed(2048)            # every rank draws the same global inputs and takes its slice
+    f0_all, control_all = torch.rand(G, 1, T, generator=gen), torch.rand(G, 2, T, generator=gen)
+    u = torch.rand(101, generator=gen).to(dev)
+    noise = torch.rand(N - 1, generator=gen).to(dev)
+    f0, control = f0_all[lo:hi].contiguous().to(dev), control_all[lo:hi].contiguous().to(dev)
+    k = 5
+    fwd, gat = [], []
+    with torch.no_grad():
+        for i in range(2 + k):
+            torch.cuda.synchronize(dev)
+            if dist is not None:
+                dist.barrier()
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            y = model(f0, control, phase_shift=u, noise=noise)
+            b.record()
+            full = gather_audio(y, G)
+            c.record()
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                fwd.append(a.elapsed_time(b))
+                gat.append(b.elapsed_time(c))
+        # parity: rows of the gathered batch that OTHER ranks rendered (first and last utterance of the job) against the
+        # same utterances rendered alone on this rank with the same draws (fp32 round-off: the reverb pairs utterances)
+        par = {}
+        for j in sorted({0, G // 2, G - 1}):
+            solo = model(f0_all[j:j + 1].to(dev), control_all[j:j + 1].to(dev), phase_shift=u, noise=noise)
+            par["row%d_vs_solo_max_abs" % j] = float((full[j] - solo[0]).abs().max())
+        shape_ok = tuple(full.shape) == (G, N)
+        del full
+    f_ms, g_ms = sum(fwd) / k, sum(gat) / k
+    tot_max, _ = aggregate_throughput(f_ms + g_ms, 0.0, dev)
+    f_max, _ = aggregate_throughput(f_ms, 0.0, dev)
+    g_max, _ = aggregate_throughput(g_ms, 0.0, dev)
+    return {"workload": "%s forward of a global batch of %d utterances x %g s sharded over %d GPU(s) + NCCL gather of the audio "
+                        "(BASELINE.json configs[4])" % ("FastNEWT" if args.variant == "fastnewt" else "NEWT", G, args.seconds, world),
+            "global_batch": G, "utterances_per_gpu": hi - lo, "n_gpus": world, "scaling": "strong", "steps": k,
+            "forward_ms_max": f_max, "gather_ms_max": g_max, "ms_per_job_max": tot_max,
+            "gather": ("ncclAllGather of [%d, %d] fp32 per rank (%.1f MB in, %.1f MB out per rank)" %
+                       (hi - lo, N, (hi - lo) * N * 4 / 1e6, G * N * 4 / 1e6)) if world > 1 else "single rank: nothing to gather",
+            "value": G * N / (tot_max * 1e-3), "value_forward_only": G * N / (f_max * 1e-3), "unit": "samples/s",
+            "gathered_shape_ok": shape_ok, "parity": par}
 
 
 def workload_config(args):
@@ -253,6 +543,18 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)
+    affinity = None
+    if world > 1:
+        # one process per GPU on one host: give every rank its own slice of the cores this job may use, so eight
+        # host threads landing 16 MB per millisecond do not migrate over (and evict each other from) the same cores
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            affinity = "%d of %d cores (%d..%d)" % (len(mine), len(cores), mine[0], mine[-1])
+        except Exception as e:   # not fatal: the numbers are still valid, only noisier
+            affinity = "unchanged (%s)" % e
 
     from neural_waveshaping_synthesis.models.modules.shaping import FastNEWT
     from neural_waveshaping_synthesis_b200 import _lib
@@ -310,13 +612,15 @@ def run_b200(args):
         for _ in range(args.warmup):
             model(f0, control)
         barrier()
-        sampler = ClockSampler(dev.index)
-        sampler.start()
+        # clocks are sampled on rank 0 only (every GPU of the box runs the same load; eight nvidia-smi loops at 20 ms
+        # were part of the host-side noise of the 8-GPU runs) and over ALL timed regions of this process
+        sampler = ClockSampler(dev.index) if rank == 0 else None
+        if sampler:
+            sampler.start()
         lib.nws_launch_count(1)
         per_step = timed_steps(args.steps, lambda: model(f0, control))
         launches = int(lib.nws_launch_count(0))
         barrier()
-        clocks = sampler.stop()
         step_ms = sum(per_step) / len(per_step)
         step_p90 = sorted(per_step)[min(len(per_step) - 1, int(0.9 * len(per_step)))]   # mean + p90
 
@@ -338,21 +642,24 @@ def run_b200(args):
         # result has landed on the host.
         from neural_waveshaping_synthesis_b200.streaming import HostPipeline
 
+        pipe = HostPipeline(model, dev)     # one pipeline: its staging buffers (device inputs, two pinned 16 MB result
+                                            # buffers) are allocated by the warm-up pass, not inside the timed region
+
         def e2e_run(n):
-            pipe = HostPipeline(model, dev)
             landed = 0
             for _, audio in pipe.run((f0_host, control_host) for _ in range(n)):
                 landed += 1
             assert landed == n and audio.shape == (B, N)
-            return pipe
 
-        e2e_run(args.warmup)
+        e2e_run(max(args.warmup, 3))
         barrier()
+        pipe.h2d_bytes = pipe.d2h_bytes = 0
         t0 = time.perf_counter()
-        pipe = e2e_run(args.steps)
+        e2e_run(args.steps)
         torch.cuda.synchronize(dev)
         e2e_s = (time.perf_counter() - t0) / args.steps
         h2d_per_step, d2h_per_step = pipe.h2d_bytes // args.steps, pipe.d2h_bytes // args.steps
+        clocks = sampler.stop() if sampler else None   # sampled over the three timed regions above (device-timed, stages, e2e)
 
         # ---- fp32 FMA issue-rate probe (the compute roofline's denominator, measured on this box)
         ffma_tflops = None
@@ -375,6 +682,27 @@ def run_b200(args):
         except Exception as e:   # the probe is informative only
             print("ffma probe failed: %s" % e, file=sys.stderr)
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    # ---- the other BASELINE configurations, inside the same line
+    configs = {}
+    if not args.no_configs:
+        clocks_mid = clocks if clocks and clocks.get("sm_mhz") else {"sm_mhz": peaks.get("sm_max_mhz", 1965.0)}
+        configs["c2"] = {"workload": "= this line's headline (`value`, `e2e`, `roofline`)",
+                         "parity_max_abs_vs_golden": {"kat_randinit_fast": parity_max_abs(model, golden_case("kat_randinit_fast"), dev)}
+                         if args.variant == "fastnewt" and args.inputs == "rand" else None}
+        if world == 1:
+            configs["c3"] = config_c3(args, cpu_model, dev, timed_steps, flush, hbm_peak, clocks_mid)
+            configs["c4"] = config_c4(args, cpu_model, dev, flush)
+        barrier()
+        configs["c5"] = config_c5(args, model, dev, rank, world, dist)
+        barrier()
+
     # ---- aggregate over ranks: time = max over ranks, samples = sum
     from neural_waveshaping_synthesis_b200.sharding import aggregate_throughput
     step_ms_max, total_samples = aggregate_throughput(step_ms, float(B * N), dev)
@@ -384,12 +712,6 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
     audio_ms = stage_acc.get("audio_fused", 0.0)
     algo_bytes = B * T * ALGO_BYTES_PER_UTT_FRAME          # 262,000 B per 4 s utterance
     achieved = algo_bytes / (audio_ms * 1e-3) / 1e9 if audio_ms > 0 else None
@@ -406,16 +728,23 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "nws_audio_tc_kernel<%s>" % ("LUT" if args.variant == "fastnewt" else "MLP"),
-                     "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "bound": "hbm", "binding_limit": "warp-instruction issue (see issue_view): the path is not HBM-bound by construction",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (achieved / hbm_peak) if achieved else None, "traffic": ncu_traffic(args.variant),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": audio_ms,
                      "kernel_share_of_step": audio_ms / sum(stage_acc.values()) if stage_acc else None,
                      "issue_view": issue_view(args.variant, audio_ms, clocks, ffma_tflops)},
         "stages_ms": stage_acc,
+        "stages_order": "serial (stage profiling disables the pipelined order; `ms_per_step` is the pipelined forward)",
+        "host_affinity": affinity,
     }
+    if configs:
+        line["configs"] = configs
     if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only
         line["cpu_baseline"] = best_cpu_baseline(cpu_model, args, T)
+        if configs.get("c4") is not None:
+            configs["c4"]["cpu_baseline"] = config_c4_cpu(cpu_model)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

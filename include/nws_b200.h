@@ -209,6 +209,10 @@ int nws_set_mlp_impl(NwsHandle handle, int impl);
  * the accumulator in TMEM (csrc/nws_audio_tc.cu), 0 = fp32 SIMT (csrc/nws_audio.cu, kept as the
  * in-library cross-check). */
 int nws_set_audio_impl(NwsHandle handle, int impl);
+/* How the fused kernel evaluates the NEWT shapers' two 8x8 hidden layers (TrainableNonlinearity, shaping.py:25-34):
+ * 1 (default) = on the tensor cores (warp-level mma m16n8k8, 3xTF32), 0 = fp32 FMA with the weights shared by lane
+ * pairs.  Both are parity-tested; the switch exists for cross-checks and measurements.                        */
+int nws_set_shaper_impl(NwsHandle handle, int impl);
 
 /* Self-test of the tcgen05 path (csrc/nws_tc.cuh): D[128,64] = A[128,K] . B[64,K]^T, 3xTF32 in TMEM,
  * K a multiple of 8 up to 104.  status[0] = 1 on completion, -1 if the MMA never signalled.

@@ -353,6 +353,12 @@ extern "C" int nws_set_audio_impl(NwsHandle ctx, int impl) {
   return NWS_OK;
 }
 
+extern "C" int nws_set_shaper_impl(NwsHandle ctx, int impl) {
+  if (!ctx || (impl != 0 && impl != 1)) { nws_set_error("nws_set_shaper_impl: impl must be 0 (fp32 FMA layers) or 1 (tensor-core 8x8 layers)"); return NWS_ERR_INVALID; }
+  ctx->shaper_impl = impl;
+  return NWS_OK;
+}
+
 extern "C" int nws_set_profiling(NwsHandle ctx, int enable) {
   if (!ctx) { nws_set_error("nws_set_profiling: NULL handle"); return NWS_ERR_INVALID; }
   if (enable && !ctx->ev[0]) {

@@ -79,3 +79,63 @@ __device__ __forceinline__ float nws_shaper_mlp(const float* __restrict__ wp, fl
   return NWS_SHAPER_SIN_INNER(a);
 }
 
+
+// The same sine-MLP for TWO samples at once with one set of weight loads: the shaper weights depend on the channel
+// only, so a thread that evaluates channel c for two samples halves the shared-memory traffic per shaper-sample
+// (the fused kernel pairs neighbouring lanes: each lane takes one channel of a channel pair for both lanes'
+// samples, see nws_audio_tc.cu).  Identical arithmetic per sample (same fma chains as nws_shaper_mlp).
+template <int MODE>
+__device__ __forceinline__ void nws_shaper_mlp2(const float* __restrict__ wp, float xa, float xb, float& ya, float& yb) {
+  const float4 hd = *reinterpret_cast<const float4*>(wp);
+  const float ua = hd.x * xa, ub = hd.x * xb;
+  float h1a[8], h1b[8], h2a[8], h2b[8];
+  {
+    const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW1), wb = *reinterpret_cast<const float4*>(wp + kShpW1 + 4);
+    const float4 ba = *reinterpret_cast<const float4*>(wp + kShpB1), bb = *reinterpret_cast<const float4*>(wp + kShpB1 + 4);
+    const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    const float b[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h1a[j] = NWS_SHAPER_SIN(fmaf(w[j], ua, b[j]));
+      h1b[j] = NWS_SHAPER_SIN(fmaf(w[j], ub, b[j]));
+    }
+  }
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(wp + kShpB2), b1 = *reinterpret_cast<const float4*>(wp + kShpB2 + 4);
+    const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW2 + j * 8), wb = *reinterpret_cast<const float4*>(wp + kShpW2 + j * 8 + 4);
+      float a = bias[j], b = bias[j];
+      a = fmaf(wa.x, h1a[0], a); a = fmaf(wa.y, h1a[1], a); a = fmaf(wa.z, h1a[2], a); a = fmaf(wa.w, h1a[3], a);
+      a = fmaf(wb.x, h1a[4], a); a = fmaf(wb.y, h1a[5], a); a = fmaf(wb.z, h1a[6], a); a = fmaf(wb.w, h1a[7], a);
+      b = fmaf(wa.x, h1b[0], b); b = fmaf(wa.y, h1b[1], b); b = fmaf(wa.z, h1b[2], b); b = fmaf(wa.w, h1b[3], b);
+      b = fmaf(wb.x, h1b[4], b); b = fmaf(wb.y, h1b[5], b); b = fmaf(wb.z, h1b[6], b); b = fmaf(wb.w, h1b[7], b);
+      h2a[j] = NWS_SHAPER_SIN_INNER(a);
+      h2b[j] = NWS_SHAPER_SIN_INNER(b);
+    }
+  }
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(wp + kShpB3), b1 = *reinterpret_cast<const float4*>(wp + kShpB3 + 4);
+    const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW3 + j * 8), wb = *reinterpret_cast<const float4*>(wp + kShpW3 + j * 8 + 4);
+      float a = bias[j], b = bias[j];
+      a = fmaf(wa.x, h2a[0], a); a = fmaf(wa.y, h2a[1], a); a = fmaf(wa.z, h2a[2], a); a = fmaf(wa.w, h2a[3], a);
+      a = fmaf(wb.x, h2a[4], a); a = fmaf(wb.y, h2a[5], a); a = fmaf(wb.z, h2a[6], a); a = fmaf(wb.w, h2a[7], a);
+      b = fmaf(wa.x, h2b[0], b); b = fmaf(wa.y, h2b[1], b); b = fmaf(wa.z, h2b[2], b); b = fmaf(wa.w, h2b[3], b);
+      b = fmaf(wb.x, h2b[4], b); b = fmaf(wb.y, h2b[5], b); b = fmaf(wb.z, h2b[6], b); b = fmaf(wb.w, h2b[7], b);
+      h1a[j] = NWS_SHAPER_SIN_INNER(a);
+      h1b[j] = NWS_SHAPER_SIN_INNER(b);
+    }
+  }
+  const float4 wa = *reinterpret_cast<const float4*>(wp + kShpW4), wb = *reinterpret_cast<const float4*>(wp + kShpW4 + 4);
+  float a = hd.y, b = hd.y;
+  a = fmaf(wa.x, h1a[0], a); a = fmaf(wa.y, h1a[1], a); a = fmaf(wa.z, h1a[2], a); a = fmaf(wa.w, h1a[3], a);
+  a = fmaf(wb.x, h1a[4], a); a = fmaf(wb.y, h1a[5], a); a = fmaf(wb.z, h1a[6], a); a = fmaf(wb.w, h1a[7], a);
+  b = fmaf(wa.x, h1b[0], b); b = fmaf(wa.y, h1b[1], b); b = fmaf(wa.z, h1b[2], b); b = fmaf(wa.w, h1b[3], b);
+  b = fmaf(wb.x, h1b[4], b); b = fmaf(wb.y, h1b[5], b); b = fmaf(wb.z, h1b[6], b); b = fmaf(wb.w, h1b[7], b);
+  ya = NWS_SHAPER_SIN_INNER(a);
+  yb = NWS_SHAPER_SIN_INNER(b);
+}

@@ -40,6 +40,53 @@ constexpr int kTcThreads = kWgs * 128 + kWgs * 32;   // + one MMA-issuing warp p
 constexpr int kWBytes = kHarmPad * kShapers * 4;       // one tf32 part of the B operand (26,624 B)
 constexpr uint32_t kLboB = 8 * 128, kSbo = 128;
 
+// Shaper weights as the tensor-core shaper path (SHP = 1) keeps them in shared memory, per channel:
+//   [2 layers][32 lanes] float4: the lane's B fragment of mma.m16n8k8 for the 8x8 layers W2 / W3 (net.2 / net.4 of
+//     TrainableNonlinearity, shaping.py:25-34): (hi(W[g][2t]), hi(W[g][2t+1]), lo(W[g][2t]), lo(W[g][2t+1])) with
+//     g = lane / 4, t = lane % 4 and hi / lo the 3xTF32 split                                      (256 floats)
+//   [4 t][24]: w1[2t], w1[2t+1], b1[2t], b1[2t+1] | (b2[2t], b2[2t+1]) x 2, twice | (b3[2t], b3[2t+1]) x 2, twice |
+//              w4[2t], w4[2t+1], b4, 0                                                             (96 floats)
+//     — the bias pairs are stored as ready-made accumulator quads (c0..c3 of the D fragment), one copy per 16-row
+//     tile, so an accumulator is initialised by one LDS.128 instead of register moves
+constexpr int kShpTcStride = 352;
+constexpr int kShpTcSmall = 256;
+constexpr int kShpTcSlot = 24;
+
+// D (16x8, fp32) += A (16x8, tf32, row) * B (8x8, tf32, col): the warp-level tensor-core instruction.  The per-channel
+// 8x8 layers of the shaper MLP are far below tcgen05's minimum tile (M = 128 needs N >= 16 and a trip through the MMA
+// warp and an mbarrier per channel-layer); mma.sync keeps operands and results in the warp's own registers.
+__device__ __forceinline__ void nws_mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// One 8x8 layer for the warp's 32 samples as two m16n8k8 tiles, 3xTF32 (small terms first).  `h` holds this thread's
+// part of the layer input in A-fragment order — h[r][u]: sample g + 8r, hidden unit 2t + u — which is also the order
+// the accumulator comes back in (D fragment: row g / g + 8, columns 2t, 2t + 1), so layers chain without any data
+// movement: the A operand's column k stands for unit 2k (k < 4) or 2(k - 4) + 1, and the B fragments are stored with
+// the same permutation.  Returns the pre-activations (bias included) in place.
+__device__ __forceinline__ void nws_shaper_layer_mma(float (&h)[4][2], const float4 bf, const float4* bias_quads) {
+  const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y), bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    uint32_t ah[4], al[4];
+    const float v[4] = {h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1]};   // a0..a3
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float hi = nws_tf32_hi(v[i]);
+      ah[i] = __float_as_uint(hi);
+      al[i] = __float_as_uint(v[i] - hi) & 0xffffe000u;
+    }
+    const float4 bq = bias_quads[mt];
+    float d[4] = {bq.x, bq.y, bq.z, bq.w};
+    nws_mma_tf32(d, al, bh0, bh1);
+    nws_mma_tf32(d, ah, bl0, bl1);
+    nws_mma_tf32(d, ah, bh0, bh1);
+    h[2 * mt][0] = d[0]; h[2 * mt][1] = d[1]; h[2 * mt + 1][0] = d[2]; h[2 * mt + 1][1] = d[3];
+  }
+}
+
 template <bool USE_LUT>
 struct TcCfg {
   static constexpr int KS = USE_LUT ? 16 : 8;                 // harmonics per A stage
@@ -52,9 +99,9 @@ struct TcCfg {
   static constexpr int oW = 0;                                // W_hi | W_lo
   static constexpr int oFilm = oW + 2 * kWBytes;              // [wg][3][256] floats
   static constexpr int oCoef = oFilm + kWgs * 3 * kFilm * 4;     // [wg][half][64][8] floats: FiLM lerp coefficients
-  static constexpr int oSmall = oCoef + kWgs * 2 * kShapers * 8 * 4;  // hmix_b[64] | shift[104] | mix_w[64] floats
-  static constexpr int oShaper = oSmall + (kShapers + kHarmPad + kShapers) * 4;
-  static constexpr int kBytes = oShaper + (USE_LUT ? 0 : kShapers * kShaperStride * 4);
+  static constexpr int oSmall = oCoef + kWgs * 2 * kShapers * 8 * 4;  // (hmix_b, mix_w)[64] | shift[104] | input_scale[64] floats
+  static constexpr int oShaper = oSmall + (kShapers + kHarmPad + kShapers + kShapers) * 4;
+  static constexpr int kBytes = oShaper + (USE_LUT ? 0 : kShapers * kShpTcStride * 4);   // (kShpTcStride >= kShaperStride)
 };
 
 __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
@@ -124,7 +171,7 @@ __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <bool USE_LUT, bool TAP, int MODE>
+template <bool USE_LUT, bool TAP, int MODE, int SHP>
 __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAudioParams p, const float* __restrict__ w_umma,
                                                                      int* __restrict__ fault) {
   using C = TcCfg<USE_LUT>;
@@ -150,9 +197,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     reinterpret_cast<float4*>(smem + C::oW)[i] = reinterpret_cast<const float4*>(w_umma)[i];
   if (tid < kShapers) sm_bw[tid] = make_float2(p.hmix_b[tid], p.mix_w[tid]);
   if (tid < kHarmPad) sm_shift[tid] = tid < kHarm ? nws_phase_shift(p.u_phase[tid], p.rand_phase[tid]) : 0.f;
-  if (!USE_LUT)
+  float* sm_scale = sm_shift + kHarmPad;                 // [64] TrainableNonlinearity.input_scale
+  if (!USE_LUT && SHP == 0)
     for (int i = tid; i < kShapers * kShaperStride / 4; i += kTcThreads)
       reinterpret_cast<float4*>(sm_shaper)[i] = reinterpret_cast<const float4*>(p.shaper)[i];
+  if (!USE_LUT && SHP == 1) {
+    if (tid < kShapers) sm_scale[tid] = p.shaper[tid * kShaperStride + kShpScale];
+    for (int i = tid; i < kShapers * 2 * 32; i += kTcThreads) {   // B fragments of the two 8x8 layers
+      const int c = i >> 6, l = (i >> 5) & 1, ln = i & 31, g = ln >> 2, t = ln & 3;
+      const float* W = p.shaper + c * kShaperStride + (l ? kShpW3 : kShpW2) + g * 8 + 2 * t;   // W[out g][in 2t, 2t+1]
+      const float w0 = W[0], w1 = W[1], h0 = nws_tf32_hi(w0), h1 = nws_tf32_hi(w1);
+      reinterpret_cast<float4*>(sm_shaper + c * kShpTcStride)[l * 32 + ln] =
+          make_float4(h0, h1, nws_tf32_lo(w0, h0), nws_tf32_lo(w1, h1));
+    }
+    for (int i = tid; i < kShapers * 4; i += kTcThreads) {
+      const int c = i >> 2, t = i & 3;
+      const float* r = p.shaper + c * kShaperStride;
+      float4* dst = reinterpret_cast<float4*>(sm_shaper + c * kShpTcStride + kShpTcSmall + t * kShpTcSlot);
+      dst[0] = make_float4(r[kShpW1 + 2 * t], r[kShpW1 + 2 * t + 1], r[kShpB1 + 2 * t], r[kShpB1 + 2 * t + 1]);
+      dst[1] = dst[2] = make_float4(r[kShpB2 + 2 * t], r[kShpB2 + 2 * t + 1], r[kShpB2 + 2 * t], r[kShpB2 + 2 * t + 1]);
+      dst[3] = dst[4] = make_float4(r[kShpB3 + 2 * t], r[kShpB3 + 2 * t + 1], r[kShpB3 + 2 * t], r[kShpB3 + 2 * t + 1]);
+      dst[5] = make_float4(r[kShpW4 + 2 * t], r[kShpW4 + 2 * t + 1], r[kShpB4], 0.f);
+    }
+  }
   if (tid < kWgs) done_s[tid] = 0;
   if (tid < 32) nws_tmem_alloc(&tmem_base_s, C::kTmemColsWg * kWgs);
   if (tid == 0) {
@@ -311,7 +378,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       lo4.x = fa[0]; lo4.y = fb[0] - fa[0];
       lo4.z = fmaf(lo4.x, bw.x, fa[kShapers]); lo4.w = fmaf(lo4.y, bw.x, fb[kShapers] - fa[kShapers]);
       hi4.x = bw.y * fa[2 * kShapers]; hi4.y = bw.y * (fb[2 * kShapers] - fa[2 * kShapers]);
-      hi4.z = 0.f; hi4.w = 0.f;
+      hi4.z = (!USE_LUT && SHP == 1) ? sm_scale[c] : 0.f; hi4.w = 0.f;   // SHP 1: the shaper's input scale rides along
       float ka = bw.y * fa[3 * kShapers], kd = bw.y * (fb[3 * kShapers] - fa[3 * kShapers]);
       float4* dst = reinterpret_cast<float4*>(sm_coef + (h * kShapers + c) * 8);
       dst[0] = lo4;
@@ -442,6 +509,93 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     const float lut_size_f = (float)lut_size;
     const float lut_min = p.lut_min, lut_span = p.lut_span, lut_rcp = p.lut_span_rcp;
     float mix_a = 0.f, mix_d = 0.f;
+    if constexpr (!USE_LUT && SHP == 1) {
+      // NEWT (shaping.py:15-37) with the two 8x8 layers of every shaper on the tensor cores (mma.sync m16n8k8, 3xTF32):
+      // 128 of the 144 multiply-adds per shaper-sample and all but 5 of the 46 weight loads leave the threads'
+      // instruction stream.  A warp's 32 samples are two 16-row tiles; thread (g = lane / 4, t = lane % 4) works on
+      // samples g + 8r (r = 0..3) and hidden units 2t, 2t + 1 — the fragment layout of the instruction — from the
+      // first layer on, so nothing is transposed between layers.  Per channel: the sample's own lane applies FiLM-in and
+      // the input scale, four shuffles hand each thread its four samples, and after the last layer a 4-lane
+      // reduce-scatter of the 8-term dot product leaves thread (g, t) with the output of sample g + 8t, whose
+      // mixdown it accumulates; one shuffle per tile returns the sums to the samples' own lanes.
+      const int g = lane >> 2, t = lane & 3;
+      float acc_a = 0.f, acc_d = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kShapers; c0 += 4) {
+        float ev[4];
+        tmem_ld<4>(tmem_lane + c0, ev);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + i;
+          if (TAP) p.exciter_out[((size_t)b * kShapers + c) * N + n] = ev[i] + sm_bw[c].x;
+          const float4 ci = cf[2 * c], cn = cf[2 * c + 1];
+          const float u = cn.z * fmaf(l1, fmaf(ci.y, ev[i], ci.w), fmaf(ci.x, ev[i], ci.z));   // input_scale * FiLM-in
+          const float* rec = sm_shaper + c * kShpTcStride;
+          const float4* sl = reinterpret_cast<const float4*>(rec + kShpTcSmall + t * kShpTcSlot);
+          const float4 s0 = sl[0], s2 = sl[5];
+          float h[4][2];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float us = __shfl_sync(0xffffffffu, u, g + 8 * r);
+            h[r][0] = NWS_SHAPER_SIN(fmaf(s0.x, us, s0.z));
+            h[r][1] = NWS_SHAPER_SIN(fmaf(s0.y, us, s0.w));
+          }
+          nws_shaper_layer_mma(h, reinterpret_cast<const float4*>(rec)[lane], sl + 1);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) { h[r][0] = NWS_SHAPER_SIN_INNER(h[r][0]); h[r][1] = NWS_SHAPER_SIN_INNER(h[r][1]); }
+          nws_shaper_layer_mma(h, reinterpret_cast<const float4*>(rec)[32 + lane], sl + 3);
+          float pr[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            pr[r] = fmaf(s2.y, NWS_SHAPER_SIN_INNER(h[r][1]), s2.x * NWS_SHAPER_SIN_INNER(h[r][0]));
+          // 4-lane reduce-scatter: thread t ends with the full dot product of sample g + 8t
+          const bool t2 = t & 2, t1 = t & 1;
+          float k0 = t2 ? pr[2] : pr[0], k1 = t2 ? pr[3] : pr[1];
+          k0 += __shfl_xor_sync(0xffffffffu, t2 ? pr[0] : pr[2], 2);
+          k1 += __shfl_xor_sync(0xffffffffu, t2 ? pr[1] : pr[3], 2);
+          const float tot = (t1 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, t1 ? k0 : k1, 1);
+          const float y = NWS_SHAPER_SIN_INNER(tot + s2.z);
+          acc_a = fmaf(cn.x, y, acc_a);
+          acc_d = fmaf(cn.y, y, acc_d);
+        }
+      }
+      const int src = 4 * (lane & 7) + (lane >> 3);   // thread (g, t) holds sample g + 8t
+      mix_a = __shfl_sync(0xffffffffu, acc_a, src);
+      mix_d = __shfl_sync(0xffffffffu, acc_d, src);
+    } else if constexpr (!USE_LUT) {
+      // NEWT (shaping.py:15-37).  The shaper weights depend on the channel only, so neighbouring lanes pair up: of
+      // the channel pair (c0, c0+1) the even lane evaluates channel c0 and the odd lane channel c0+1, each for BOTH
+      // lanes' samples — one set of weight loads per two shaper-samples (the loop was shared-memory-pipe bound at 46
+      // broadcast LDS.128 per shaper-sample), at the price of one shuffle per channel pair.  FiLM-in is applied by
+      // the sample's own lane before the exchange; the FiLM-out / mixdown coefficients depend on (half hop, channel)
+      // and both lanes are in the same half hop, so each lane accumulates its channel's contribution to both samples
+      // and the two partial mixdowns are swapped back once per tile.
+      const bool odd = lane & 1;
+      float own_a = 0.f, own_d = 0.f, oth_a = 0.f, oth_d = 0.f;   // partial mixdowns: own sample / the partner lane's
+#pragma unroll 1
+      for (int c0 = 0; c0 < kShapers; c0 += 2) {
+        float ev[2];
+        tmem_ld<2>(tmem_lane + c0, ev);
+        float x[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = c0 + i;
+          if (TAP) p.exciter_out[((size_t)b * kShapers + c) * N + n] = ev[i] + sm_bw[c].x;
+          const float4 ci = cf[2 * c];
+          x[i] = fmaf(l1, fmaf(ci.y, ev[i], ci.w), fmaf(ci.x, ev[i], ci.z));
+        }
+        const float mine = odd ? x[1] : x[0];
+        const float theirs = __shfl_xor_sync(0xffffffffu, odd ? x[0] : x[1], 1);   // the partner's sample, this lane's channel
+        const int c = c0 + (odd ? 1 : 0);
+        float y_own, y_oth;
+        nws_shaper_mlp2<MODE>(sm_shaper + c * kShaperStride, mine, theirs, y_own, y_oth);
+        const float2 cn = *reinterpret_cast<const float2*>(&cf[2 * c + 1]);
+        own_a = fmaf(cn.x, y_own, own_a); own_d = fmaf(cn.y, y_own, own_d);
+        oth_a = fmaf(cn.x, y_oth, oth_a); oth_d = fmaf(cn.y, y_oth, oth_d);
+      }
+      mix_a = own_a + __shfl_xor_sync(0xffffffffu, oth_a, 1);
+      mix_d = own_d + __shfl_xor_sync(0xffffffffu, oth_d, 1);
+    } else {
 #pragma unroll 1
     for (int c0 = 0; c0 < kShapers; c0 += C::kChPerLd) {
       float ev[C::kChPerLd];
@@ -456,24 +610,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
         const float4 ci = cf[2 * c];
         const float2 cn = *reinterpret_cast<const float2*>(&cf[2 * c + 1]);
         const float x = fmaf(l1, fmaf(ci.y, ev[i], ci.w), fmaf(ci.x, ev[i], ci.z));
-        float y;
-        if (USE_LUT) {
-          // FastNEWT.shaping_fn (shaping.py:136-151): same index arithmetic as nws_lut_index — floor and clamp
-          // done on the integer side (F2I.FLOOR saturates, NaN -> 0 with a NaN fract, as floorf/fmaxf/fminf give);
-          // the table row holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
-          // MODE 2 (size 4096 = 2^12): the multiply by the size is folded into the division's constants — scaling
-          // by a power of two commutes with every rounding of the Markstein sequence, so idx is bit-identical
-          const float idx = MODE == 2 ? nws_lut_idx_pow2(x, lut_min, lut_span * (1.0f / 4096.0f), lut_rcp * 4096.0f)
-                                      : nws_div_markstein(NWS_MUL(lut_size_f, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
-          const int fi = nws_min_relu(__float2int_rd(idx), lut_size - 1);   // clamp to [0, size-1]: one VIMNMX.RELU
-          const float2 t2 = __ldg(lut_row + i * lut_size + (uint32_t)fi);
-          y = fmaf(t2.y, NWS_ADD(idx, -(float)fi), t2.x);
-        } else {
-          y = nws_shaper_mlp<MODE>(sm_shaper + c * kShaperStride, x);
-        }
+        // FastNEWT.shaping_fn (shaping.py:136-151): same index arithmetic as nws_lut_index — floor and clamp
+        // done on the integer side (F2I.FLOOR saturates, NaN -> 0 with a NaN fract, as floorf/fmaxf/fminf give);
+        // the table row holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
+        // MODE 2 (size 4096 = 2^12): the multiply by the size is folded into the division's constants — scaling
+        // by a power of two commutes with every rounding of the Markstein sequence, so idx is bit-identical
+        const float idx = MODE == 2 ? nws_lut_idx_pow2(x, lut_min, lut_span * (1.0f / 4096.0f), lut_rcp * 4096.0f)
+                                    : nws_div_markstein(NWS_MUL(lut_size_f, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
+        const int fi = nws_min_relu(__float2int_rd(idx), lut_size - 1);   // clamp to [0, size-1]: one VIMNMX.RELU
+        const float2 t2 = __ldg(lut_row + i * lut_size + (uint32_t)fi);
+        const float y = fmaf(t2.y, NWS_ADD(idx, -(float)fi), t2.x);
         mix_a = fmaf(cn.x, y, mix_a);
         mix_d = fmaf(cn.y, y, mix_d);
       }
+    }
     }
     nws_tc_fence_before();   // TMEM reads ordered before the next tile's first MMA (via the warpgroup barrier)
     float o = fmaf(l1, mix_d + mix_kd, mix_a + mix_ka) + mix_b;
@@ -489,6 +639,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   nws_tc_fence_before();
   __syncthreads();
   if (tid < 32) nws_tmem_dealloc(tmem_base_s, C::kTmemColsWg * kWgs);
+}
+
+// one instantiation: opt in to its dynamic shared memory once per device, launch
+template <bool USE_LUT, bool TAP, int MODE, int SHP>
+int launch_variant(const NwsAudioParams& p, const float* wu, int* fault, int grid, cudaStream_t s) {
+  static bool attr_done[64] = {};
+  if (nws_first_use_on_device(attr_done))
+    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<USE_LUT, TAP, MODE, SHP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TcCfg<USE_LUT>::kBytes));
+  nws_audio_tc_kernel<USE_LUT, TAP, MODE, SHP><<<grid, kTcThreads, TcCfg<USE_LUT>::kBytes, s>>>(p, wu, fault);
+  return NWS_OK;
 }
 
 }  // namespace
@@ -510,16 +671,6 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   p.tile_chunk = chunk_env >= 1 && chunk_env <= 64 ? chunk_env : kTileChunk;
   NWS_CUDA_OK(cudaMemsetAsync(tile_counter, 0, sizeof(int), s));
 
-  static bool attr_done[64] = {};
-  if (nws_first_use_on_device(attr_done)) {
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
-    NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::kBytes));
-  }
   const long long tiles = (long long)B * (t_end - t_begin);
   if (tiles >= (1ll << 31) - 4096 || t_end <= t_begin) { nws_set_error("nws_launch_audio_tc: bad tile count"); return NWS_ERR_INVALID; }
   p.hops_magic = (uint32_t)((1ull << 32) / (uint64_t)(t_end - t_begin) > 0xffffffffull ? 0xffffffffull : (1ull << 32) / (uint64_t)(t_end - t_begin));
@@ -528,13 +679,21 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   const int grid = (int)(want < cap ? want : cap);
   const float* wu = w + ctx->lay.hmix_umma;
   const bool direct = ctx->shaper_inner_bound <= 8.0f;   // see NWS_SHAPER_SIN_INNER
-  if (use_lut && !exciter_out && ctx->lut_size == 4096) nws_audio_tc_kernel<true, false, 2><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, ctx->fault_dev);
-  else if (use_lut && !exciter_out) nws_audio_tc_kernel<true, false, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, ctx->fault_dev);
-  else if (use_lut) nws_audio_tc_kernel<true, true, 1><<<grid, kTcThreads, TcCfg<true>::kBytes, s>>>(p, wu, ctx->fault_dev);
-  else if (!exciter_out && direct) nws_audio_tc_kernel<false, false, 2><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, ctx->fault_dev);
-  else if (!exciter_out) nws_audio_tc_kernel<false, false, 1><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, ctx->fault_dev);
-  else if (direct) nws_audio_tc_kernel<false, true, 2><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, ctx->fault_dev);
-  else nws_audio_tc_kernel<false, true, 1><<<grid, kTcThreads, TcCfg<false>::kBytes, s>>>(p, wu, ctx->fault_dev);
+  const bool tap = exciter_out != nullptr;
+  const int shp = ctx->shaper_impl;
+  int rc;
+  if (use_lut) {
+    if (!tap && ctx->lut_size == 4096) rc = launch_variant<true, false, 2, 0>(p, wu, ctx->fault_dev, grid, s);
+    else if (!tap) rc = launch_variant<true, false, 1, 0>(p, wu, ctx->fault_dev, grid, s);
+    else rc = launch_variant<true, true, 1, 0>(p, wu, ctx->fault_dev, grid, s);
+  } else if (shp) {
+    if (!tap) rc = direct ? launch_variant<false, false, 2, 1>(p, wu, ctx->fault_dev, grid, s) : launch_variant<false, false, 1, 1>(p, wu, ctx->fault_dev, grid, s);
+    else rc = direct ? launch_variant<false, true, 2, 1>(p, wu, ctx->fault_dev, grid, s) : launch_variant<false, true, 1, 1>(p, wu, ctx->fault_dev, grid, s);
+  } else {
+    if (!tap) rc = direct ? launch_variant<false, false, 2, 0>(p, wu, ctx->fault_dev, grid, s) : launch_variant<false, false, 1, 0>(p, wu, ctx->fault_dev, grid, s);
+    else rc = direct ? launch_variant<false, true, 2, 0>(p, wu, ctx->fault_dev, grid, s) : launch_variant<false, true, 1, 0>(p, wu, ctx->fault_dev, grid, s);
+  }
+  if (rc) return rc;
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }

@@ -112,6 +112,7 @@ struct NwsContext {
   int mlp_tc_off[11] = {};
   float shaper_inner_bound = 1e30f;   // max_j(|b_j| + sum_i |W_ji|) over shaper layers 2-4 (set by nws_load_weights)
   int audio_impl = 1;          // 1 = tcgen05 harmonic mixer (nws_audio_tc.cu), 0 = fp32 SIMT (nws_audio.cu)
+  int shaper_impl = 1;         // NEWT shaper layers inside nws_audio_tc_kernel: 1 = mma.sync 8x8 layers, 0 = fp32 FMA (paired lanes)
   int device = 0;
   // mbarrier-timeout flag of the tcgen05 kernels: one int in mapped pinned host memory (the kernels write it
   // only on a timeout; every API call reads the host side without a synchronise and fails with NWS_ERR_CUDA)

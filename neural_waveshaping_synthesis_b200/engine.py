@@ -182,6 +182,10 @@ class NwsEngine:
         """1 = tcgen05 harmonic mixer (default), 0 = fp32 SIMT mixer."""
         _lib.check(self.lib.nws_set_audio_impl(self.handle, impl))
 
+    def set_shaper_impl(self, impl: int):
+        """NEWT shaper hidden layers: 1 = tensor cores (mma.sync, default), 0 = fp32 FMA (paired lanes)."""
+        _lib.check(self.lib.nws_set_shaper_impl(self.handle, impl))
+
     def set_pipeline(self, enable: bool):
         """Pipelined forward (GRU time blocks on an internal stream overlapped with rendering); default on."""
         _lib.check(self.lib.nws_set_pipeline(self.handle, 1 if enable else 0))

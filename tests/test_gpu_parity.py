@@ -337,6 +337,27 @@ def test_full_size_newt_batch_vs_oracle(tag):
         assert e[0] < tmax and e[1] < trms, (tag, row, e)
 
 
+@pytest.mark.parametrize("case,tag", [("kat_vn_newt", "vn"), ("kat_randinit_newt", "randinit"), ("small_vn_newt", "vn")])
+def test_newt_shaper_impls_agree(case, tag):
+    """The NEWT shapers' hidden layers on the tensor cores (mma.sync m16n8k8, 3xTF32: the default) and as fp32 FMAs with
+    weights shared by lane pairs (nws_set_shaper_impl(0)): both within the stated tolerance of the reference's golden
+    output, and within 3xTF32 round-off of each other."""
+    m, w = _model(tag, False)
+    c = load_case(case)
+    args = (c["f0"].cuda(), c["control"].cuda())
+    kw = dict(phase_shift=c["u_phase"].cuda(), noise=c["noise"].cuda())
+    tmax, trms = _tols(tag)
+    outs = []
+    with torch.no_grad():
+        for impl in (1, 0):
+            m._engine_for(args[0]).set_shaper_impl(impl)
+            y = m(*args, **kw)
+            e = err(y, c["out"])
+            assert e[0] < tmax and e[1] < trms, (case, impl, e)
+            outs.append(y)
+    assert err(outs[0], outs[1])[0] < 5e-6, err(outs[0], outs[1])
+
+
 def test_model_copy_after_forward_and_foreign_shapes():
     """(1) deepcopy / torch.save of a model that has run (its engines hold ctypes handles) work and the copy
     renders the same audio through its own handle; (2) a model built with other hyper-parameters than newt.gin's is
