@@ -418,8 +418,9 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   const int M = B * T, N = T * kHop;
 
   const int n_blocks = (T + 127) / 128;
+  const int gru_ctas = B;   // SMs the recurrence occupies (one utterance per CTA)
   const bool pipelined = ctx->pipeline && ctx->mlp_impl && ctx->audio_impl && !ctx->profile && ctx->enc_stream &&
-                         ctx->aux_stream && n_blocks >= 3 && (long long)B * T >= 4096 && B + 16 <= ctx->sm_count;
+                         ctx->aux_stream && n_blocks >= 3 && (long long)B * T >= 4096 && gru_ctas + 16 <= ctx->sm_count;
   const int t_split = 128, early_end = t_split - 1;   // pipelined: hops [0,127) only need FiLM frames 0..127
   if (pipelined) {
     // The GRU is T dependent steps on B SMs; everything downstream only needs the frames already encoded.
@@ -461,7 +462,7 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
     NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_ready, s));
     NWS_CUDA_OK(cudaStreamWaitEvent(aux, ctx->ev_early_ready, 0));
     NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, early_end, w.counters,
-                                use_lut, aux, ctx->sm_count - B));
+                                use_lut, aux, ctx->sm_count - gru_ctas));
     NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_done, aux));
     g_tl.mark("audio head", aux);
     // the rest, once everything is encoded; its audio overlaps the tail of the early launch
