@@ -369,7 +369,8 @@ def config_c4(args, cpu_model, dev, flush):
     import torch
     from neural_waveshaping_synthesis.models.modules.shaping import FastNEWT
     out = {"workload": "B = 1 buffer sweep (BASELINE.json configs[3]; scripts/time_buffer_sizes.py:13,66-75)",
-           "timing": "CUDA events per call on the launch stream; `cold` = 256 MiB L2 flush before every call, `warm` = back to back",
+           "timing": "CUDA events per call on the launch stream; `cold` = 256 MiB L2 flush before every call, `warm` = back to back, "
+                     "`graph_replay` = the forward captured once into a CUDA graph (no per-call host work ahead of the first kernel)",
            "sizes": BUFFER_SIZES, "stream_sizes": STREAM_SIZES}
     iters = 40
     sweep = golden_case  # noqa: F841
@@ -402,8 +403,34 @@ def config_c4(args, cpu_model, dev, flush):
                     return [a.elapsed_time(b) for a, b in evs]
 
                 cold, warm = run(True), run(False)
+                # the same forward captured once into a CUDA graph and replayed: device-side latency of the launch
+                # chain without the per-call host work (Python, ctypes, torch.empty) ahead of the first kernel
+                graph_ms = None
+                try:
+                    # (draws injected: reserving a range of torch's generator is host work that cannot be captured)
+                    u_g, nz_g = torch.rand(101, device=dev), torch.rand(HOP * T - 1, device=dev)
+                    model(f0, control, phase_shift=u_g, noise=nz_g)
+                    torch.cuda.synchronize(dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        y_static = model(f0, control, phase_shift=u_g, noise=nz_g)
+                    g.replay()
+                    torch.cuda.synchronize(dev)
+                    evs = []
+                    for _ in range(iters):
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        g.replay()
+                        b.record()
+                        evs.append((a, b))
+                    torch.cuda.synchronize(dev)
+                    graph_ms = statistics.median([a.elapsed_time(b) for a, b in evs])
+                    del g, y_static
+                except Exception as e:   # informative only
+                    print("graph capture failed at bs %d: %s" % (bs, e), file=sys.stderr)
                 rows[str(bs)] = {"ms_median_cold": statistics.median(cold), "ms_p90_cold": pctl(cold, 0.9),
                                  "ms_median_warm": statistics.median(warm), "ms_p90_warm": pctl(warm, 0.9),
+                                 "ms_median_graph_replay": graph_ms,
                                  "rtf_warm": statistics.median(warm) * 1e-3 / (bs / SR)}
             # stateful streaming: pushes of bs samples (bs / 128 frames) into one running stream
             stream_rows = {}

@@ -213,6 +213,12 @@ int nws_set_audio_impl(NwsHandle handle, int impl);
  * 1 (default) = on the tensor cores (warp-level mma m16n8k8, 3xTF32), 0 = fp32 FMA with the weights shared by lane
  * pairs.  Both are parity-tested; the switch exists for cross-checks and measurements.                        */
 int nws_set_shaper_impl(NwsHandle handle, int impl);
+/* Reverb.forward (shaping.py:161-173) for buffers of up to 4096 samples (and for streaming pushes of up to 33 hops):
+ * 1 (default) = direct-form convolution in one launch (csrc/nws_reverb_direct.cu), 0 = always the FFT path.       */
+int nws_set_reverb_direct(NwsHandle handle, int enable);
+/* Hop-rate MLP chain for up to 40 frames per utterance (and up to 32 utterances): 1 (default) = fp32 small-batch chain,
+ * 2 CTAs per utterance (csrc/nws_mlp_small.cu); 0 = always the 128-frame-tile tensor-core kernel.                  */
+int nws_set_small_path(NwsHandle handle, int enable);
 
 /* Self-test of the tcgen05 path (csrc/nws_tc.cuh): D[128,64] = A[128,K] . B[64,K]^T, 3xTF32 in TMEM,
  * K a multiple of 8 up to 104.  status[0] = 1 on completion, -1 if the MMA never signalled.

@@ -106,6 +106,10 @@ def load_library():
         L.nws_stage_control_to_params.restype = c_int
         L.nws_set_audio_impl.argtypes = [vp, c_int]
         L.nws_set_audio_impl.restype = c_int
+        L.nws_set_small_path.argtypes = [vp, c_int]
+        L.nws_set_small_path.restype = c_int
+        L.nws_set_reverb_direct.argtypes = [vp, c_int]
+        L.nws_set_reverb_direct.restype = c_int
         L.nws_set_shaper_impl.argtypes = [vp, c_int]
         L.nws_set_shaper_impl.restype = c_int
         L.nws_selftest_umma.argtypes = [vp, vp, vp, c_int, c_int, vp, vp]
@@ -160,7 +164,7 @@ EXPORTED_SYMBOLS = [
     "nws_stream_create", "nws_stream_destroy", "nws_stream_reset", "nws_stream_window", "nws_stream_push",
     "nws_loudness_workspace_bytes", "nws_extract_loudness", "nws_extract_rms", "nws_selftest_ffma_peak",
     "nws_tensor_numel", "nws_status", "nws_interp_frames_len", "nws_interp_frames",
-    "nws_set_shaper_impl",
+    "nws_set_shaper_impl", "nws_set_reverb_direct", "nws_set_small_path",
 ]
 
 # Shapes the kernels are built for (gin/models/newt.gin) in TENSOR_KEYS order.  The C side reads

@@ -58,6 +58,10 @@ extern "C" int nws_create(const NwsConfig* cfg, NwsHandle* out) {
   e = cudaHostAlloc((void**)&ctx->fault_host, sizeof(int), cudaHostAllocMapped);
   if (e == cudaSuccess) { *ctx->fault_host = 0; e = cudaHostGetDevicePointer((void**)&ctx->fault_dev, ctx->fault_host, 0); }
   if (e != cudaSuccess) { nws_set_error("nws_create: %s", cudaGetErrorString(e)); nws_destroy(ctx); return NWS_ERR_CUDA; }
+  e = cudaMalloc(&ctx->dir_counters, (kDirCounters + 4) * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->dir_counters, 0, (kDirCounters + 4) * sizeof(int));
+  ctx->tile_counters = ctx->dir_counters ? ctx->dir_counters + kDirCounters : nullptr;
+  if (e != cudaSuccess) { nws_set_error("nws_create: %s", cudaGetErrorString(e)); nws_destroy(ctx); return NWS_ERR_CUDA; }
   int rc = nws_make_twiddle_master(ctx);
   if (rc) { nws_destroy(ctx); return rc; }
   // internal encoder stream + fork/join events of the pipelined forward (timing disabled: cheaper)
@@ -93,6 +97,7 @@ extern "C" int nws_destroy(NwsHandle ctx) {
   cudaFree(ctx->lut);
   cudaFree(ctx->lut2);
   cudaFree(ctx->tw_master);
+  cudaFree(ctx->dir_counters);
   if (ctx->fault_host) cudaFreeHost(ctx->fault_host);
   delete ctx;
   return NWS_OK;
@@ -335,7 +340,9 @@ extern "C" int nws_stage_control_to_params(NwsHandle ctx, const float* control, 
   cudaStream_t s = (cudaStream_t)stream;
   const int M = B * T;
   NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, T, nullptr, s));
-  if (ctx->mlp_impl) {
+  if (ctx->mlp_impl && nws_mlp_small_ok(ctx, B, T)) {
+    NWS_TRY(nws_launch_mlp_small(ctx, w.hbuf, w.film, w.bands, B, T, s));
+  } else if (ctx->mlp_impl) {
     NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, 0, T, s));
   } else {
     NWS_TRY(nws_launch_linear(w.hbuf, ctx->packed + ctx->lay.proj_wt, ctx->packed + ctx->lay.proj_b, nullptr, nullptr,
@@ -350,6 +357,18 @@ extern "C" int nws_stage_control_to_params(NwsHandle ctx, const float* control, 
 extern "C" int nws_set_audio_impl(NwsHandle ctx, int impl) {
   if (!ctx || (impl != 0 && impl != 1)) { nws_set_error("nws_set_audio_impl: impl must be 0 (fp32 SIMT mixer) or 1 (tcgen05 mixer)"); return NWS_ERR_INVALID; }
   ctx->audio_impl = impl;
+  return NWS_OK;
+}
+
+extern "C" int nws_set_small_path(NwsHandle ctx, int enable) {
+  if (!ctx) { nws_set_error("nws_set_small_path: NULL handle"); return NWS_ERR_INVALID; }
+  ctx->small_path = enable != 0;
+  return NWS_OK;
+}
+
+extern "C" int nws_set_reverb_direct(NwsHandle ctx, int enable) {
+  if (!ctx) { nws_set_error("nws_set_reverb_direct: NULL handle"); return NWS_ERR_INVALID; }
+  ctx->reverb_direct = enable != 0;
   return NWS_OK;
 }
 
@@ -442,6 +461,29 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
     g_tl.mark("gru rest", g);
   }
 
+  // Short buffers (the sweep of scripts/time_buffer_sizes.py: 2..32 frames): latency is launches, not work.  One launch
+  // does everything that precedes the MLP chain — the draws, the phase carries, the noise spectrum and the recurrence
+  // run side by side as CTA roles — then the cluster MLP chain (which also filters the noise), the audio kernel and the
+  // direct-form reverb: 4 launches instead of 12.
+  const bool small = !pipelined && ctx->small_path && ctx->mlp_impl && ctx->audio_impl &&
+                     nws_front_ok(B, T) && nws_mlp_small_ok(ctx, B, T);
+  if (small) {
+    NWS_STAGE(ctx, kStGru, s, nws_launch_front(ctx, control, ctrl_channels, w.hbuf, f0, w.carry, noise, u_phase ? nullptr : w.u_phase,
+                                               seed, offset, w.xspec, B, T, s));
+    if (!u_phase) u_phase = w.u_phase;
+    // (the noise chain's cluster also filters the noise: the band gains never leave shared memory)
+    NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_mlp_small(ctx, w.hbuf, w.film, nullptr, B, T, s, w.xspec, w.dry, 0, T));
+    NWS_STAGE(ctx, kStAudio, s, nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, T,
+                                                    ctx->tile_counters, use_lut, s));
+    const size_t small_rev_bytes = (size_t)((B + 1) / 2) * nws_reverb_fft_len(N) * sizeof(float2);
+    if (ctx->reverb_direct && nws_reverb_direct_ok(ctx, B, N, small_rev_bytes)) {
+      NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb_direct(ctx, w.dry, out, (float*)w.rev, B, N, s));
+    } else {
+      NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb(ctx, w.dry, out, w.rev, B, N, s));
+    }
+    return NWS_OK;
+  }
+
   if (!u_phase || !noise) {  // the forward's own draws (generators.py:55, :30); injected ones are kept
     NWS_STAGE(ctx, kStRng, s, nws_launch_rng(u_phase ? nullptr : w.u_phase, noise ? nullptr : w.noise, N - 1, seed, offset, s));
     if (!u_phase) u_phase = w.u_phase;
@@ -461,7 +503,7 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
     g_tl.mark("mlp+noise head", s);
     NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_ready, s));
     NWS_CUDA_OK(cudaStreamWaitEvent(aux, ctx->ev_early_ready, 0));
-    NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, early_end, w.counters,
+    NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, early_end, ctx->tile_counters + 2,
                                 use_lut, aux, ctx->sm_count - gru_ctas));
     NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_done, aux));
     g_tl.mark("audio head", aux);
@@ -472,12 +514,15 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
     NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, t_split, T, s));
     g_tl.mark("noise rest", s);
     NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, early_end, T,
-                                w.counters + 1, use_lut, s));
+                                ctx->tile_counters, use_lut, s));
     g_tl.mark("audio rest", s);
     NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_early_done, 0));
   } else {
     NWS_STAGE(ctx, kStGru, s, nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, T, nullptr, s));
-    if (ctx->mlp_impl) {
+    if (ctx->mlp_impl && nws_mlp_small_ok(ctx, B, T)) {
+      // a handful of frames: fp32 chain, 2 CTAs per utterance, no 128-frame tile to pad
+      NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_mlp_small(ctx, w.hbuf, w.film, w.bands, B, T, s));
+    } else if (ctx->mlp_impl) {
       // projection + both TimeDistributedMLPs in one tensor-core kernel (activations stay in TMEM)
       NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, 0, T, s));
     } else {
@@ -489,10 +534,15 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
     // noise branch -> dry
     NWS_STAGE(ctx, kStNoiseFilter, s, nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, 0, T, s));
     // fused audio-rate kernel: dry = newt(exciter) + noise
-    NWS_STAGE(ctx, kStAudio, s, launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, w.counters, use_lut, s));
+    NWS_STAGE(ctx, kStAudio, s, launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, ctx->tile_counters, use_lut, s));
   }
-  // reverb
-  NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb(ctx, w.dry, out, w.rev, B, N, s));
+  // reverb: direct form for short buffers (one launch instead of three 32000-point passes), FFT otherwise
+  const size_t rev_bytes = (size_t)((B + 1) / 2) * nws_reverb_fft_len(N) * sizeof(float2);
+  if (ctx->reverb_direct && nws_reverb_direct_ok(ctx, B, N, rev_bytes)) {
+    NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb_direct(ctx, w.dry, out, (float*)w.rev, B, N, s));
+  } else {
+    NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb(ctx, w.dry, out, w.rev, B, N, s));
+  }
   if (g_tl.on) { g_tl.mark("reverb", s); g_tl.dump(); }
   return NWS_OK;
 }
@@ -574,7 +624,7 @@ extern "C" int nws_stage_audio(NwsHandle ctx, const float* f0, const float* film
   cudaStream_t s = (cudaStream_t)stream;
   NWS_TRY(nws_launch_bct_to_rows(film, w.film, B, kFilm, T, kFilm, s));
   NWS_TRY(nws_launch_phase_carry(f0, w.carry, B, T, s));
-  return launch_audio(ctx, f0, w.carry, w.film, u_phase, nullptr, newt_out, exciter_out, B, T, w.counters, use_lut, s);
+  return launch_audio(ctx, f0, w.carry, w.film, u_phase, nullptr, newt_out, exciter_out, B, T, ctx->tile_counters, use_lut, s);
 }
 
 extern "C" int nws_stage_noise(NwsHandle ctx, const float* H, const float* noise, float* out, int B, int T,
@@ -597,5 +647,7 @@ extern "C" int nws_stage_reverb(NwsHandle ctx, const float* x, float* out, int B
   if (!need) { nws_set_error("nws_stage_reverb: N = %d too long", N); return NWS_ERR_UNSUPPORTED; }
   if (workspace_bytes < need) { nws_set_error("nws_stage_reverb: workspace too small (%zu < %zu)", workspace_bytes, need); return NWS_ERR_WORKSPACE; }
   float2* work = (float2*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  if (ctx->reverb_direct && nws_reverb_direct_ok(ctx, B, N, need - 256))
+    return nws_launch_reverb_direct(ctx, x, out, (float*)work, B, N, (cudaStream_t)stream);
   return nws_launch_reverb(ctx, x, out, work, B, N, (cudaStream_t)stream);
 }

@@ -34,7 +34,7 @@ struct NwsAudioParams {
   float* exciter_out;     // [B][64][N] or null
   int B, T;
   int t_begin, t_end;     // hop range [t_begin, t_end) rendered by this launch (whole utterance: 0, T)
-  int* tile_counter;      // device int, zero at launch: dynamic tile scheduler of nws_audio_tc_kernel
+  int* tile_counter;      // {tiles claimed, CTAs done}: both zero at launch, reset by the last CTA (dynamic tile scheduler)
   int tile_chunk;         // tiles per scheduler claim (consecutive hops), >= 1
   uint32_t hops_magic;    // floor(2^32 / (t_end - t_begin)), saturated: tile -> (utterance, hop) without a division
 };

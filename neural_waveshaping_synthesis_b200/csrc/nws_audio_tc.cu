@@ -638,6 +638,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   if (!ok && fault) *(volatile int*)fault = 1;   // mapped host memory: a plain store, no atomic over PCIe
   nws_tc_fence_before();
   __syncthreads();
+  // The scheduler's counter pair {tiles claimed, CTAs done} lives in the context and is zero between launches: the last
+  // CTA to leave puts it back (no memset launch per forward; safe under CUDA-graph replay, unlike a host-side toggle).
+  if (tid == 0 && atomicAdd(p.tile_counter + 1, 1) == (int)gridDim.x - 1) {
+    p.tile_counter[0] = 0;
+    p.tile_counter[1] = 0;
+  }
   if (tid < 32) nws_tmem_dealloc(tmem_base_s, C::kTmemColsWg * kWgs);
 }
 
@@ -669,7 +675,6 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   p.t_begin = t_begin; p.t_end = t_end; p.tile_counter = tile_counter;
   static const int chunk_env = getenv("NWS_TILE_CHUNK") ? atoi(getenv("NWS_TILE_CHUNK")) : 0;   // development knob
   p.tile_chunk = chunk_env >= 1 && chunk_env <= 64 ? chunk_env : kTileChunk;
-  NWS_CUDA_OK(cudaMemsetAsync(tile_counter, 0, sizeof(int), s));
 
   const long long tiles = (long long)B * (t_end - t_begin);
   if (tiles >= (1ll << 31) - 4096 || t_end <= t_begin) { nws_set_error("nws_launch_audio_tc: bad tile count"); return NWS_ERR_INVALID; }

@@ -21,6 +21,10 @@ constexpr int kBandsPad = 132;         // row stride of the noise-band / spectru
 constexpr int kIr = 256;
 constexpr int kReverbIr = 32000;       // [0, ir] (shaping.py:162)
 constexpr int kShaperStride = 176;     // packed floats per shaper (172 used)
+constexpr int kSmallMlpMaxFrames = 40;  // frames per utterance the small-batch MLP chain takes (nws_mlp_small.cu)
+constexpr int kSmallMlpMaxBatch = 32;
+constexpr int kReverbDirectMaxN = 4096; // buffers up to this length take the direct-form reverb (nws_reverb_direct.cu)
+constexpr int kDirCounters = 4096;     // completion counters of the direct-form reverb (utterances x output blocks)
 
 // packed per-shaper record (floats): all vector groups 16-byte aligned
 constexpr int kShpScale = 0, kShpB4 = 1, kShpW1 = 4, kShpB1 = 12, kShpW2 = 20, kShpB2 = 84, kShpW3 = 92,
@@ -116,6 +120,10 @@ struct NwsContext {
   int device = 0;
   // mbarrier-timeout flag of the tcgen05 kernels: one int in mapped pinned host memory (the kernels write it
   // only on a timeout; every API call reads the host side without a synchronise and fails with NWS_ERR_CUDA)
+  int* tile_counters = nullptr; // [4] = two {tiles claimed, CTAs done} pairs of nws_audio_tc_kernel's scheduler (main / early launch)
+  int* dir_counters = nullptr; // [kDirCounters] zero between launches (nws_reverb_direct.cu)
+  int small_path = 1;          // few frames: 1 = fp32 small-batch MLP chain (nws_mlp_small.cu), 0 = always the 128-frame-tile kernel
+  int reverb_direct = 1;       // short buffers: 1 = direct-form reverb, 0 = always the FFT path
   int* fault_host = nullptr;
   int* fault_dev = nullptr;
   // pipelined forward: the GRU runs in time blocks on an internal stream while the main stream renders the
@@ -219,6 +227,10 @@ int nws_launch_build_lut(const NwsContext* ctx, const float* points, float* lut,
 int nws_launch_pack_weights(NwsContext* ctx, const float* const* tensors, cudaStream_t s);
 // nws_noise.cu
 int nws_launch_noise_spectrum(const NwsContext* ctx, const float* noise, float2* xspec, int T, cudaStream_t s);
+bool nws_front_ok(int B, int T);
+int nws_launch_front(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, const float* f0,
+                     double* carry, const float* noise_in, float* u_phase_out, uint64_t seed, uint64_t offset,
+                     float2* xspec, int B, int T, cudaStream_t s);
 int nws_launch_noise_filter(const NwsContext* ctx, const float* bands, const float2* xspec, float* out, int B, int T,
                             int hop_begin, int hop_end, cudaStream_t s);
 // nws_reverb.cu
@@ -227,3 +239,15 @@ int nws_launch_reverb(NwsContext* ctx, const float* x, float* out, float2* work,
 void nws_reverb_free_plans(NwsContext* ctx);
 void nws_reverb_invalidate(NwsContext* ctx);
 int nws_make_twiddle_master(NwsContext* ctx);
+// nws_mlp_small.cu
+bool nws_mlp_small_ok(const NwsContext* ctx, int B, int T);
+int nws_launch_mlp_small(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int B, int T, cudaStream_t s,
+                         const float2* xspec = nullptr, float* dry = nullptr, int hop_begin = 0, int hop_end = 0);
+// nws_reverb_direct.cu
+size_t nws_reverb_direct_scratch_bytes(int B, int N);
+bool nws_reverb_direct_ok(const NwsContext* ctx, int B, int N, size_t scratch_bytes);
+int nws_launch_reverb_direct(NwsContext* ctx, const float* x, float* out, float* scratch, int B, int N, cudaStream_t s);
+size_t nws_reverb_direct_causal_scratch_bytes(int B, int n_new_max);
+int nws_launch_reverb_direct_causal(NwsContext* ctx, const float* hist, const float* dry, size_t dry_stride, int first_sample,
+                                    float* out, float* hist_next, float* scratch, int B, int n_new, int apply_reverb,
+                                    cudaStream_t s);

@@ -10,21 +10,27 @@
 //   * two real 256-point frames share one complex FFT (frame a in the real part, b in the imaginary).
 // istft with a rectangular window is overlap-add divided by the frame-count envelope {1,2}.
 #include "nws_fft.cuh"
+#include "nws_hop_bodies.cuh"
 #include "nws_internal.cuh"
-
-__device__ __forceinline__ void nws_load_tw256(float2* tw_s, const float2* __restrict__ tw_master, int tid, int nthreads) {
-  for (int i = tid; i < 128; i += nthreads) tw_s[i] = tw_master[i * (kTwMaster / 256)];
-}
+#include "nws_noise_bodies.cuh"
 
 // X[t][k] = rfft(xp[128 t : 128 t + 256])[k], xp = reflect_pad(noise, 128)   (generators.py:31).
-// One CTA per pair of frames.
-__global__ void __launch_bounds__(128) nws_noise_spectrum_kernel(const float* __restrict__ noise, int n_noise,
-                                                                 const float2* __restrict__ tw_master,
-                                                                 float2* __restrict__ xspec, int T) {
+// One CTA per pair of frames (all `nthreads` threads of the CTA must call).  `noise` null: the samples are this
+// forward's own draw (generators.py:30), generated in place from the Philox stream (seed, offset) exactly as
+// nws_rng_kernel would have written them.
+__device__ __forceinline__ float nws_noise_sample(const float* __restrict__ noise, int idx, uint64_t seed, uint64_t offset) {
+  if (noise) return noise[idx];
+  const NwsPhilox4 r = nws_philox4x32_10(offset + (uint64_t)(idx >> 2), 1ull, seed);
+  return nws_u32_to_unit(r.v[idx & 3]);
+}
+
+__device__ __forceinline__ void nws_noise_spectrum_body(int pair, int nthreads, const float* __restrict__ noise, int n_noise,
+                                                        uint64_t seed, uint64_t offset, const float2* __restrict__ tw_master,
+                                                        float2* __restrict__ xspec, int T) {
   __shared__ float2 buf_a[256], buf_b[256], tw_s[128];
-  const int tid = threadIdx.x, ta = 2 * blockIdx.x, tb = ta + 1;
-  nws_load_tw256(tw_s, tw_master, tid, 128);
-  for (int n = tid; n < 256; n += 128) {
+  const int tid = threadIdx.x, ta = 2 * pair, tb = ta + 1;
+  nws_load_tw256(tw_s, tw_master, tid, nthreads);
+  for (int n = tid; n < 256; n += nthreads) {
     float v[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -32,13 +38,13 @@ __global__ void __launch_bounds__(128) nws_noise_spectrum_kernel(const float* __
       int idx = t * kHop + n - kIr / 2;               // index into the unpadded noise
       if (idx < 0) idx = -idx;                        // reflect (no edge repeat)
       if (idx >= n_noise) idx = 2 * (n_noise - 1) - idx;
-      v[q] = t < T ? noise[idx] : 0.f;
+      v[q] = t < T ? nws_noise_sample(noise, idx, seed, offset) : 0.f;
     }
     buf_a[n] = make_float2(v[0], v[1]);
   }
   __syncthreads();
-  const float2* z = nws_fft_smem<false, false>(buf_a, buf_b, tw_s, 1, 8, 0, tid, 128);
-  for (int k = tid; k <= 128; k += 128) {
+  const float2* z = nws_fft_smem<false, false>(buf_a, buf_b, tw_s, 1, 8, 0, tid, nthreads);
+  for (int k = tid; k <= 128; k += nthreads) {
     const float2 zk = z[k], zc = z[(256 - k) & 255];
     // Xa = (Z[k] + conj(Z[N-k])) / 2 ; Xb = (Z[k] - conj(Z[N-k])) / (2i)
     const float2 xa = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
@@ -48,81 +54,106 @@ __global__ void __launch_bounds__(128) nws_noise_spectrum_kernel(const float* __
   }
 }
 
+__global__ void __launch_bounds__(128) nws_noise_spectrum_kernel(const float* __restrict__ noise, int n_noise,
+                                                                 const float2* __restrict__ tw_master,
+                                                                 float2* __restrict__ xspec, int T) {
+  nws_noise_spectrum_body(blockIdx.x, 128, noise, n_noise, 0ull, 0ull, tw_master, xspec, T);
+}
+
 int nws_launch_noise_spectrum(const NwsContext* ctx, const float* noise, float2* xspec, int T, cudaStream_t s) {
   nws_noise_spectrum_kernel<<<(T + 1) / 2, 128, 0, s>>>(noise, kHop * T - 1, ctx->tw_master, xspec, T);
   NWS_LAUNCH_CHECK();
   return NWS_OK;
 }
 
-// One CTA = one utterance x kNoiseHops output hops.  It filters frames t0-1 .. t0+kNoiseHops-1
-// (kNoiseHops+1 frames = (kNoiseHops+1)/2 complex FFTs, two at a time), keeps their 256-sample
-// outputs in shared memory and overlap-adds them into the kNoiseHops hops it owns.
-constexpr int kNoiseHops = 15;
-constexpr int kNoiseFrames = kNoiseHops + 1;
+// ------------------------------------------------------------------------------------------------
+// Front end of the short-buffer path in ONE launch: everything of a forward that does not depend on the encoder's
+// output, next to the encoder itself.  CTA roles by block index:
+//   [0, B)       the GRU recurrence of utterance b                                  (nws_gru_body)
+//   [B, 2B)      the fp64 phase carries of utterance b: eight threads per hop (every partial sum of float32 values in
+//                double is exact at audio-range f0, so any grouping gives the bits of nws_phase_carry_kernel)
+//   [2B, ...)    one pair of noise frames each: the forward's draws (Philox, when none are injected) and the noise
+//                spectrum; the first of them also writes the 101 phase-shift draws
+// Replaces four launches (draws, carries, spectrum, GRU) of ~2.5-8.5 us each by one of ~8.5 us.
+struct NwsFrontParams {
+  const float *w_hh, *w_ih, *b_ih, *b_hh, *control;
+  int ctrl_channels;
+  float* hbuf;
+  int B, T;
+  const float* f0;
+  double* carry;
+  const float* noise_in;    // injected noise draw or null
+  float* u_phase_out;       // where to write the phase-shift draw, or null (injected)
+  uint64_t seed, offset;
+  const float2* tw_master;
+  float2* xspec;
+};
+
+__global__ void __launch_bounds__(kGates, 1) nws_front_kernel(const NwsFrontParams p) {
+  const int role = blockIdx.x, tid = threadIdx.x, T = p.T;
+  if (role < p.B) {
+    nws_gru_body(role, p.w_hh, p.w_ih, p.b_ih, p.b_hh, p.control, p.ctrl_channels, p.hbuf, T, 0, T, nullptr);
+  } else if (role < 2 * p.B) {
+    __shared__ double hop_sum[kSmallMlpMaxFrames + 8];
+    const int b = role - p.B, t = tid >> 3, part = tid & 7;
+    const float* f = p.f0 + (size_t)b * T;
+    const float inv_hop = (float)T / (float)(T * kHop);
+    double s = 0.0;
+    if (t < T) {
+      const float fm = f[t > 0 ? t - 1 : 0], fc = f[t], fp = f[t + 1 < T ? t + 1 : T - 1];
+      for (int r = part * 16; r < part * 16 + 16; ++r) {
+        const NwsLerp c = nws_lerp_coords(t * kHop + r, T, inv_hop);
+        const float x0 = c.i0 == t ? fc : (c.i0 < t ? fm : fp);
+        const float x1 = c.i1 == t ? fc : (c.i1 < t ? fm : fp);
+        s += (double)nws_lerp_apply(c, x0, x1);
+      }
+    }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (t < T && part == 0) hop_sum[t] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double run = 0.0;
+      for (int i = 0; i < T; ++i) {
+        p.carry[(size_t)b * T + i] = run;
+        run += hop_sum[i];
+      }
+    }
+  } else {
+    const int pair = role - 2 * p.B;
+    if (pair == 0 && p.u_phase_out && tid < (kHarm + 3) / 4) {
+      const NwsPhilox4 r = nws_philox4x32_10(p.offset + (uint64_t)tid, 0ull, p.seed);
+      for (int j = 0; j < 4; ++j)
+        if (4 * tid + j < kHarm) p.u_phase_out[4 * tid + j] = nws_u32_to_unit(r.v[j]);
+    }
+    nws_noise_spectrum_body(pair, kGates, p.noise_in, kHop * T - 1, p.seed, p.offset, p.tw_master, p.xspec, T);
+  }
+}
+
+bool nws_front_ok(int B, int T) { return T >= 2 && T <= kSmallMlpMaxFrames && B >= 1 && B <= kSmallMlpMaxBatch; }
+
+int nws_launch_front(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, const float* f0,
+                     double* carry, const float* noise_in, float* u_phase_out, uint64_t seed, uint64_t offset,
+                     float2* xspec, int B, int T, cudaStream_t s) {
+  NwsFrontParams p{};
+  const float* w = ctx->packed;
+  p.w_hh = w + ctx->lay.gru_whh; p.w_ih = w + ctx->lay.gru_wih; p.b_ih = w + ctx->lay.gru_bih; p.b_hh = w + ctx->lay.gru_bhh;
+  p.control = control; p.ctrl_channels = ctrl_channels; p.hbuf = hbuf; p.B = B; p.T = T;
+  p.f0 = f0; p.carry = carry; p.noise_in = noise_in; p.u_phase_out = u_phase_out; p.seed = seed; p.offset = offset;
+  p.tw_master = ctx->tw_master; p.xspec = xspec;
+  nws_front_kernel<<<2 * B + (T + 1) / 2, kGates, 0, s>>>(p);
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}
 
 __global__ void __launch_bounds__(256) nws_noise_filter_kernel(const float* __restrict__ bands,
                                                                const float2* __restrict__ xspec,
                                                                const float2* __restrict__ tw_master,
                                                                float* __restrict__ out, int T, int hop_begin,
                                                                int hop_end) {
-  __shared__ float2 buf_a[2][256], buf_b[2][256], tw_s[128];
-  __shared__ float hs[2][2][kBandsPad];           // [fft][frame of pair][band]
-  __shared__ float y_s[kNoiseFrames][256];
-  const int tid = threadIdx.x, b = blockIdx.y, t0 = hop_begin + blockIdx.x * kNoiseHops;   // hops [hop_begin, hop_end)
-  const int g = tid >> 7, j = tid & 127;          // g: which of the two concurrent FFTs
-  const int f_lim = hop_end < T ? hop_end : T;    // frames >= hop_end are not needed (and may not be encoded yet)
-  nws_load_tw256(tw_s, tw_master, tid, 256);
-
-  for (int pair0 = 0; pair0 < kNoiseFrames / 2; pair0 += 2) {
-    const int pair = pair0 + g;
-    const int fa = t0 - 1 + 2 * pair, fb = fa + 1;  // frame indices of this FFT's pair
-    __syncthreads();
-    for (int q = 0; q < 2; ++q) {
-      const int f = q == 0 ? fa : fb;
-      for (int k = j; k < kBandsPad; k += 128)
-        hs[g][q][k] = (f >= 0 && f < f_lim && k < kBands) ? bands[((size_t)b * T + f) * kBandsPad + k] : 0.f;
-    }
-    __syncthreads();
-    // Z[k] = Ya[k] + i Yb[k], Y = X * Hw, Hermitian-extended to 256 bins
-    for (int k = j; k < 256; k += 128) {
-      const int kk = k <= 128 ? k : 256 - k;
-      const int km = kk == 0 ? 1 : kk - 1, kp = kk == 128 ? 127 : kk + 1;
-      const float sgn = (kk & 1) ? -1.f : 1.f;
-      float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
-      if (fa >= 0 && fa < f_lim) {
-        const float hw = sgn * fmaf(0.25f, hs[g][0][km] + hs[g][0][kp], 0.5f * hs[g][0][kk]);
-        const float2 x = xspec[(size_t)fa * kBandsPad + kk];
-        ya = make_float2(x.x * hw, x.y * hw);
-      }
-      if (fb >= 0 && fb < f_lim) {
-        const float hw = sgn * fmaf(0.25f, hs[g][1][km] + hs[g][1][kp], 0.5f * hs[g][1][kk]);
-        const float2 x = xspec[(size_t)fb * kBandsPad + kk];
-        yb = make_float2(x.x * hw, x.y * hw);
-      }
-      if (kk == 0 || kk == 128) { ya.y = 0.f; yb.y = 0.f; }  // irfft ignores the imaginary part of DC / Nyquist
-      if (k > 128) { ya.y = -ya.y; yb.y = -yb.y; }            // conj for the mirrored half
-      buf_a[g][k] = make_float2(ya.x - yb.y, ya.y + yb.x);
-    }
-    __syncthreads();
-    // both FFTs advance in lock-step (the helper's barriers are CTA-wide)
-    const float2* z = nws_fft_smem<true, false>(&buf_a[0][0], &buf_b[0][0], tw_s, 1, 8, 1, tid, 256);
-    for (int n = j; n < 256; n += 128) {
-      const float2 v = z[g * 256 + n];
-      y_s[2 * pair][n] = v.x * (1.0f / 256.0f);
-      y_s[2 * pair + 1][n] = v.y * (1.0f / 256.0f);
-    }
-  }
-  __syncthreads();
-  // overlap-add: hop t takes the first half of frame t and the second half of frame t-1, divided by
-  // the number of overlapping frames (1 in the first hop, else 2)
-  const int N = T * kHop;
-  for (int i = tid; i < kNoiseHops * kHop; i += 256) {
-    const int h = i >> 7, r = i & 127, t = t0 + h;
-    if (t >= hop_end) break;
-    const float cur = y_s[h + 1][r];
-    const float v = t == 0 ? cur : 0.5f * (y_s[h][kHop + r] + cur);
-    out[(size_t)b * N + t * kHop + r] = v;
-  }
+  const int b = blockIdx.y;
+  nws_noise_filter_body(bands + (size_t)b * T * kBandsPad, xspec, tw_master, out + (size_t)b * T * kHop, T, hop_begin, hop_end,
+                        blockIdx.x);
 }
 
 int nws_launch_noise_filter(const NwsContext* ctx, const float* bands, const float2* xspec, float* out, int B, int T,

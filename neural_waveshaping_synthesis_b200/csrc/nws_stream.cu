@@ -38,7 +38,10 @@ struct NwsStreamState {
   float* h_state;     // [B][128]
   double* phase_sum;  // [B]
   float* u_phase;     // [kHarmPad]
-  float* rev_hist;    // [B][kReverbIr] last dry samples
+  float* rev_hist;    // [B][kReverbIr] last dry samples (the current one of the two ping-pong buffers below)
+  float* rev_hist_buf[2];
+  float* dir_scratch; // partial sums of the direct-form reverb (streams of short pushes), or null
+  int dir_n_new_max;
   // per-push window
   float* f0_w;        // [B][Tw]
   float* ctrl_w;      // [B][2][Tw]
@@ -154,7 +157,7 @@ __global__ void nws_stream_finish_kernel(const float* __restrict__ xw, const flo
 extern "C" int nws_stream_destroy(NwsStreamHandle st) {
   if (!st) return NWS_OK;
   cudaFree(st->f0_h); cudaFree(st->ctrl_h); cudaFree(st->hrow_h); cudaFree(st->h_state); cudaFree(st->phase_sum);
-  cudaFree(st->u_phase); cudaFree(st->rev_hist); cudaFree(st->f0_w); cudaFree(st->ctrl_w); cudaFree(st->noise_w);
+  cudaFree(st->u_phase); cudaFree(st->rev_hist_buf[0]); cudaFree(st->rev_hist_buf[1]); cudaFree(st->dir_scratch); cudaFree(st->f0_w); cudaFree(st->ctrl_w); cudaFree(st->noise_w);
   cudaFree(st->ws_base); cudaFree(st->xw); cudaFree(st->yw); cudaFree(st->rev_work);
   delete st;
   return NWS_OK;
@@ -179,7 +182,12 @@ extern "C" int nws_stream_create(NwsHandle ctx, int B, int max_frames, NwsStream
   alloc((void**)&st->h_state, (size_t)B * kEmb * sizeof(float));
   alloc((void**)&st->phase_sum, (size_t)B * sizeof(double));
   alloc((void**)&st->u_phase, kHarmPad * sizeof(float));
-  alloc((void**)&st->rev_hist, (size_t)B * kReverbIr * sizeof(float));
+  alloc((void**)&st->rev_hist_buf[0], (size_t)B * kReverbIr * sizeof(float));
+  alloc((void**)&st->rev_hist_buf[1], (size_t)B * kReverbIr * sizeof(float));
+  st->rev_hist = st->rev_hist_buf[0];
+  // short pushes (up to 33 hops) take the direct-form reverb: one launch instead of an overlap-save FFT over 32000 + n points
+  st->dir_n_new_max = kHop * (max_frames + 1) <= kReverbDirectMaxN + kHop ? kHop * (max_frames + 1) : 0;
+  if (st->dir_n_new_max) alloc((void**)&st->dir_scratch, nws_reverb_direct_causal_scratch_bytes(B, st->dir_n_new_max));
   alloc((void**)&st->f0_w, (size_t)B * st->Tw_max * sizeof(float));
   alloc((void**)&st->ctrl_w, (size_t)B * 2 * st->Tw_max * sizeof(float));
   alloc((void**)&st->noise_w, (size_t)kHop * st->Tw_max * sizeof(float));
@@ -253,7 +261,6 @@ extern "C" int nws_stream_push(NwsStreamHandle st, const float* f0, const float*
   if (n_out <= 0) return NWS_OK;
 
   // hop-rate chain over the window, then the rendered hops [r0, r1)
-  NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, Tw, 0, Tw, s));
   const float* noise = noise_window;
   if (!noise) {
     // noise[i] of the stream is Philox block (offset + i/4): the window starts at sample 128 * g_base
@@ -261,15 +268,31 @@ extern "C" int nws_stream_push(NwsStreamHandle st, const float* f0, const float*
     noise = st->noise_w;
   }
   NWS_TRY(nws_launch_noise_spectrum(ctx, noise, w.xspec, Tw, s));
-  NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, Tw, r0, r1, s));
+  if (nws_mlp_small_ok(ctx, B, Tw)) {
+    // short pushes: cluster MLP chain with the noise filter fused (band gains stay in shared memory)
+    NWS_TRY(nws_launch_mlp_small(ctx, w.hbuf, w.film, nullptr, B, Tw, s, w.xspec, w.dry, r0, r1));
+  } else {
+    NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, Tw, 0, Tw, s));
+    NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, Tw, r0, r1, s));
+  }
   nws_stream_carry_kernel<<<B, 128, (size_t)n_out * sizeof(double), s>>>(st->f0_w, w.carry, st->phase_sum, Tw, r0, r1);
   NWS_LAUNCH_CHECK();
-  NWS_TRY(nws_launch_audio_tc(ctx, st->f0_w, w.carry, w.film, st->u_phase, w.dry, w.dry, nullptr, B, Tw, r0, r1, w.counters,
+  NWS_TRY(nws_launch_audio_tc(ctx, st->f0_w, w.carry, w.film, st->u_phase, w.dry, w.dry, nullptr, B, Tw, r0, r1, ctx->tile_counters,
                               use_lut, s));
   st->n_rendered += n_out;
 
-  // reverb as a causal convolution: overlap-save over [32000 past dry samples | new], keep the new part
+  // reverb as a causal convolution over [32000 past dry samples | new], keep the new part
   const int n_new = n_out * kHop, Nx = kReverbIr + n_new;
+  if (ctx->reverb_direct && st->dir_scratch && n_new <= st->dir_n_new_max) {
+    // direct form: convolution, dry add and the history shift in ONE launch (nws_reverb_direct.cu)
+    float* next = st->rev_hist == st->rev_hist_buf[0] ? st->rev_hist_buf[1] : st->rev_hist_buf[0];
+    NWS_TRY(nws_launch_reverb_direct_causal(ctx, st->rev_hist, w.dry, (size_t)Nw, r0 * kHop, out, next, st->dir_scratch, B, n_new,
+                                            apply_reverb, s));
+    st->rev_hist = next;
+    *n_out_frames = n_out;
+    return NWS_OK;
+  }
+  // FFT form: overlap-save through the four-step transform
   dim3 grid((Nx + 255) / 256 < 64 ? (Nx + 255) / 256 : 64, B);
   nws_stream_assemble_kernel<<<grid, 256, 0, s>>>(st->rev_hist, w.dry, Nw, r0 * kHop, n_new, st->xw);
   NWS_LAUNCH_CHECK();

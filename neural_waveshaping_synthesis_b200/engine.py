@@ -182,6 +182,14 @@ class NwsEngine:
         """1 = tcgen05 harmonic mixer (default), 0 = fp32 SIMT mixer."""
         _lib.check(self.lib.nws_set_audio_impl(self.handle, impl))
 
+    def set_small_path(self, enable: bool):
+        """Few frames per utterance: fp32 small-batch MLP chain (default) or always the tensor-core tile kernel."""
+        _lib.check(self.lib.nws_set_small_path(self.handle, 1 if enable else 0))
+
+    def set_reverb_direct(self, enable: bool):
+        """Short buffers: direct-form reverb (default) or always the FFT path."""
+        _lib.check(self.lib.nws_set_reverb_direct(self.handle, 1 if enable else 0))
+
     def set_shaper_impl(self, impl: int):
         """NEWT shaper hidden layers: 1 = tensor cores (mma.sync, default), 0 = fp32 FMA (paired lanes)."""
         _lib.check(self.lib.nws_set_shaper_impl(self.handle, impl))

@@ -10,6 +10,6 @@ c = d.get('configs', {})
 if 'c3' in c: print('c3', c['c3']['ms_per_step'], c['c3']['roofline']['kernel_ms'], c['c3']['parity_max_abs_vs_golden'], c['c3']['roofline'].get('sfu_view'))
 if 'c4' in c:
     for v in ('fastnewt', 'newt'):
-        print('c4', v, {k: round(r['ms_median_warm'], 4) for k, r in c['c4'][v]['stateless_forward'].items()}, {k: round(r['ms_median'], 4) for k, r in c['c4'][v]['stream_push'].items()}, c['c4'][v]['parity_max_abs_vs_golden'])
+        print('c4', v, {k: (round(r['ms_median_warm'], 4), round(r['ms_median_graph_replay'] or 0, 4)) for k, r in c['c4'][v]['stateless_forward'].items()}, {k: round(r['ms_median'], 4) for k, r in c['c4'][v]['stream_push'].items()}, c['c4'][v]['parity_max_abs_vs_golden'])
 if 'c5' in c: print('c5', c['c5'])
 P

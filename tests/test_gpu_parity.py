@@ -115,21 +115,35 @@ def test_sin_variants():
     assert eq < 6e-7 and et.max().item() < 1e-6 and et.pow(2).mean().sqrt().item() < 2.5e-7
 
 
-@pytest.mark.parametrize("impl", [1, 0])   # 1 = tcgen05 MLP chain (default), 0 = fp32 SIMT layers
+# default = tcgen05 MLP chain for many frames + fp32 small-batch chain (nws_mlp_small.cu) for a handful;
+# tc = the tcgen05 chain for every size; simt = the fp32 per-layer kernels
+@pytest.mark.parametrize("path", ["default", "tc", "simt"])
 @pytest.mark.parametrize("tag", ["randinit", "vn"])
-def test_control_to_params(tag, impl, eng_rand, eng_vn):
+def test_control_to_params(tag, path, eng_rand, eng_vn):
     """The whole hop-rate chain: control -> FiLM parameters and noise band gains."""
     eng, w = eng_rand if tag == "randinit" else eng_vn
     c = load_case("small_%s_newt" % tag)
-    eng.set_mlp_impl(impl)
+    eng.set_mlp_impl(0 if path == "simt" else 1)
+    eng.set_small_path(path == "default")
     try:
         film, bands = eng.control_to_params(c["control"].cuda())
         # a batch that spans several 128-frame tiles with a ragged tail
         gen = torch.Generator().manual_seed(9)
         big = torch.rand(3, 2, 171, generator=gen)
         film_b, bands_b = eng.control_to_params(big.cuda())
+        # the small-batch chain at its limits: 40 frames, odd frame counts, one frame
+        for B, T in ((5, 40), (1, 33), (2, 1)):
+            small = torch.rand(B, 2, T, generator=gen)
+            fs, bs = eng.control_to_params(small.cuda()) if T > 1 else (None, None)
+            if fs is not None:
+                es = oracle.control_module(w, small)
+                rfs, rbs = oracle.td_mlp(w, "newt.mlp", es), oracle.td_mlp(w, "h_generator", es)
+                tol_s = 3e-5 if tag == "randinit" else 2e-3
+                assert err(fs, rfs)[0] < tol_s * max(1.0, float(rfs.abs().max())), (path, B, T)
+                assert err(bs, rbs)[0] < tol_s * max(1.0, float(rbs.abs().max())), (path, B, T)
     finally:
         eng.set_mlp_impl(1)
+        eng.set_small_path(True)
     tol = 3e-5 if tag == "randinit" else 2e-3   # vn: the GRU's recurrent rounding dominates (see test_control_embedding)
     assert err(film, c["part_film"])[0] < tol * max(1.0, float(c["part_film"].abs().max()))
     assert err(bands, c["part_H"])[0] < tol * max(1.0, float(c["part_H"].abs().max()))
@@ -217,14 +231,24 @@ def test_noise_branch(tag, eng_rand, eng_vn):
 
 # 768 .. 32000: exact-length plan 125 x 256; 32768: exact 128 x 256; 33024, 96000: zero-padded power-of-two plan
 # with the wrap folded back; 64000: exact 250 x 256 (the benchmark configs)
-@pytest.mark.parametrize("tag,N", [("randinit", 768), ("vn", 1280), ("vn", 4096), ("vn", 32000), ("vn", 32768),
-                                   ("vn", 33024), ("vn", 64000), ("vn", 96000)])
-def test_reverb(tag, N, eng_rand, eng_vn):
+# up to 4096 samples the default is the direct-form convolution (nws_reverb_direct.cu): 128 (one partial tile), 256, 768,
+# 1280, 4096 (16 x 16 tiles); "fft" forces the transform path at those sizes too
+@pytest.mark.parametrize("tag,N,direct", [("randinit", 128, True), ("vn", 256, True), ("randinit", 768, True), ("vn", 1280, True),
+                                          ("vn", 4096, True), ("randinit", 768, False), ("vn", 1280, False), ("vn", 4096, False),
+                                          ("vn", 4224, True), ("vn", 32000, True), ("vn", 32768, True),
+                                          ("vn", 33024, True), ("vn", 64000, True), ("vn", 96000, True)])
+def test_reverb(tag, N, direct, eng_rand, eng_vn):
     eng, w = eng_rand if tag == "randinit" else eng_vn
     gen = torch.Generator().manual_seed(N)
     x = torch.randn(3, N, generator=gen) * 0.1
     ref = oracle.reverb(w, x)
-    y = eng.reverb(x.cuda())
+    eng.set_reverb_direct(direct)
+    try:
+        y = eng.reverb(x.cuda())
+        y2 = eng.reverb(x.cuda())
+    finally:
+        eng.set_reverb_direct(True)
+    assert torch.equal(y, y2)          # partial sums are combined in a fixed order: repeat runs are bit-identical
     e = err(y, ref)
     assert e[0] < 1e-5 * max(1.0, float(ref.abs().max())), (e, float(ref.abs().max()))
     lit = oracle.reverb_literal(w["reverb.ir"].numpy(), x.numpy())
@@ -635,9 +659,11 @@ def test_stream_equals_whole_utterance(tag, fast, chunks):
         "last", where[-1].tolist() if where.numel() else None)
 
 
-def test_stream_long_reverb_history():
+@pytest.mark.parametrize("direct", [True, False])   # direct-form reverb per push (default for <= 33 hops) / overlap-save FFT
+def test_stream_long_reverb_history(direct):
     """More than 32000 samples through the stream: the reverb history buffer wraps several times."""
     m, w = _model("vn", True)
+    m._engine_for(torch.empty(0, device="cuda:0")).set_reverb_direct(direct)
     T, n = 320, 32                                   # 40960 samples in 10 pushes
     f0, control = oracle.realistic_inputs(T, w["data_mean"].numpy(), w["data_std"].numpy(), B=1)
     u, noise = oracle.draw_rng(T, 3)
