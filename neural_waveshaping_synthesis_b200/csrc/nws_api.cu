@@ -468,16 +468,18 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   const bool small = !pipelined && ctx->small_path && ctx->mlp_impl && ctx->audio_impl &&
                      nws_front_ok(B, T) && nws_mlp_small_ok(ctx, B, T);
   if (small) {
+    static const bool no_pdl = getenv("NWS_NO_PDL") != nullptr;   // development switch: ordinary launches
+    const bool pdl = !ctx->profile && !no_pdl;
     NWS_STAGE(ctx, kStGru, s, nws_launch_front(ctx, control, ctrl_channels, w.hbuf, f0, w.carry, noise, u_phase ? nullptr : w.u_phase,
                                                seed, offset, w.xspec, B, T, s));
     if (!u_phase) u_phase = w.u_phase;
     // (the noise chain's cluster also filters the noise: the band gains never leave shared memory)
-    NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_mlp_small(ctx, w.hbuf, w.film, nullptr, B, T, s, w.xspec, w.dry, 0, T));
+    NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_mlp_small(ctx, w.hbuf, w.film, nullptr, B, T, s, w.xspec, w.dry, 0, T, pdl));
     NWS_STAGE(ctx, kStAudio, s, nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, T,
-                                                    ctx->tile_counters, use_lut, s));
+                                                    ctx->tile_counters, use_lut, s, 0, pdl));
     const size_t small_rev_bytes = (size_t)((B + 1) / 2) * nws_reverb_fft_len(N) * sizeof(float2);
     if (ctx->reverb_direct && nws_reverb_direct_ok(ctx, B, N, small_rev_bytes)) {
-      NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb_direct(ctx, w.dry, out, (float*)w.rev, B, N, s));
+      NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb_direct(ctx, w.dry, out, (float*)w.rev, B, N, s, pdl));
     } else {
       NWS_STAGE(ctx, kStReverb, s, nws_launch_reverb(ctx, w.dry, out, w.rev, B, N, s));
     }

@@ -232,6 +232,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   nws_tc_fence_before();
   __syncthreads();
   nws_tc_fence_after();
+  // Short-buffer path (programmatic dependent launch): everything above overlapped the MLP chain's launch; its FiLM rows
+  // and filtered noise are read from here on.  No-ops for ordinary launches.
+  nws_pdl_wait();
+  nws_pdl_launch();
   const uint32_t tmem_acc = tmem_base_s + (wg & 3) * C::kTmemColsWg;     // this warpgroup's columns
   const uint32_t tmem_lane = tmem_acc + ((uint32_t)(wwarp * 32) << 16);   // this warp's lane quarter
   const uint32_t idesc = nws_umma_idesc_tf32(128, 64);
@@ -649,12 +653,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
 
 // one instantiation: opt in to its dynamic shared memory once per device, launch
 template <bool USE_LUT, bool TAP, int MODE, int SHP>
-int launch_variant(const NwsAudioParams& p, const float* wu, int* fault, int grid, cudaStream_t s) {
+int launch_variant(const NwsAudioParams& p, const float* wu, int* fault, int grid, cudaStream_t s, bool pdl) {
   static bool attr_done[64] = {};
   if (nws_first_use_on_device(attr_done))
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<USE_LUT, TAP, MODE, SHP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TcCfg<USE_LUT>::kBytes));
-  nws_audio_tc_kernel<USE_LUT, TAP, MODE, SHP><<<grid, kTcThreads, TcCfg<USE_LUT>::kBytes, s>>>(p, wu, fault);
+  if (!pdl) {
+    nws_audio_tc_kernel<USE_LUT, TAP, MODE, SHP><<<grid, kTcThreads, TcCfg<USE_LUT>::kBytes, s>>>(p, wu, fault);
+    return NWS_OK;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = TcCfg<USE_LUT>::kBytes; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int n_attr = 0;
+  nws_pdl_config(&cfg, attr, &n_attr, true);
+  NWS_CUDA_OK(cudaLaunchKernelEx(&cfg, nws_audio_tc_kernel<USE_LUT, TAP, MODE, SHP>, p, wu, fault));
   return NWS_OK;
 }
 
@@ -662,7 +675,7 @@ int launch_variant(const NwsAudioParams& p, const float* wu, int* fault, int gri
 
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
-                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s, int max_ctas) {
+                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s, int max_ctas, bool pdl) {
   NwsAudioParams p{};
   const float* w = ctx->packed;
   p.f0 = f0; p.carry = carry; p.film = film; p.u_phase = u_phase;
@@ -688,15 +701,15 @@ int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* ca
   const int shp = ctx->shaper_impl;
   int rc;
   if (use_lut) {
-    if (!tap && ctx->lut_size == 4096) rc = launch_variant<true, false, 2, 0>(p, wu, ctx->fault_dev, grid, s);
-    else if (!tap) rc = launch_variant<true, false, 1, 0>(p, wu, ctx->fault_dev, grid, s);
-    else rc = launch_variant<true, true, 1, 0>(p, wu, ctx->fault_dev, grid, s);
+    if (!tap && ctx->lut_size == 4096) rc = launch_variant<true, false, 2, 0>(p, wu, ctx->fault_dev, grid, s, pdl);
+    else if (!tap) rc = launch_variant<true, false, 1, 0>(p, wu, ctx->fault_dev, grid, s, pdl);
+    else rc = launch_variant<true, true, 1, 0>(p, wu, ctx->fault_dev, grid, s, pdl);
   } else if (shp) {
-    if (!tap) rc = direct ? launch_variant<false, false, 2, 1>(p, wu, ctx->fault_dev, grid, s) : launch_variant<false, false, 1, 1>(p, wu, ctx->fault_dev, grid, s);
-    else rc = direct ? launch_variant<false, true, 2, 1>(p, wu, ctx->fault_dev, grid, s) : launch_variant<false, true, 1, 1>(p, wu, ctx->fault_dev, grid, s);
+    if (!tap) rc = direct ? launch_variant<false, false, 2, 1>(p, wu, ctx->fault_dev, grid, s, pdl) : launch_variant<false, false, 1, 1>(p, wu, ctx->fault_dev, grid, s, pdl);
+    else rc = direct ? launch_variant<false, true, 2, 1>(p, wu, ctx->fault_dev, grid, s, pdl) : launch_variant<false, true, 1, 1>(p, wu, ctx->fault_dev, grid, s, pdl);
   } else {
-    if (!tap) rc = direct ? launch_variant<false, false, 2, 0>(p, wu, ctx->fault_dev, grid, s) : launch_variant<false, false, 1, 0>(p, wu, ctx->fault_dev, grid, s);
-    else rc = direct ? launch_variant<false, true, 2, 0>(p, wu, ctx->fault_dev, grid, s) : launch_variant<false, true, 1, 0>(p, wu, ctx->fault_dev, grid, s);
+    if (!tap) rc = direct ? launch_variant<false, false, 2, 0>(p, wu, ctx->fault_dev, grid, s, pdl) : launch_variant<false, false, 1, 0>(p, wu, ctx->fault_dev, grid, s, pdl);
+    else rc = direct ? launch_variant<false, true, 2, 0>(p, wu, ctx->fault_dev, grid, s, pdl) : launch_variant<false, true, 1, 0>(p, wu, ctx->fault_dev, grid, s, pdl);
   }
   if (rc) return rc;
   NWS_LAUNCH_CHECK();

@@ -198,6 +198,26 @@ inline bool nws_first_use_on_device(bool* flags) {
     }                                                                                       \
   } while (0)
 
+// ------------------------------------------------------------------ programmatic dependent launch (short-buffer path)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: everything before nws_pdl_wait() (weight staging, TMEM allocation, barrier set-up) overlaps
+// the predecessor; nws_pdl_wait() returns when the predecessor grid has completed and its writes are visible;
+// nws_pdl_launch() lets the NEXT kernel of the stream start its own prologue.  Both are no-ops for ordinary launches.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void nws_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void nws_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+// launch configuration with (optionally) the programmatic-serialization attribute; `attr` must outlive the launch call
+inline void nws_pdl_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int* n_attr, bool pdl) {
+  if (pdl) {
+    attr[*n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[*n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++*n_attr;
+  }
+  cfg->attrs = attr;
+  cfg->numAttrs = *n_attr;
+}
+
 // ------------------------------------------------------------------ kernel launchers (one per .cu)
 // nws_encoder.cu
 int nws_launch_phase_carry(const float* f0, double* carry, int B, int T, cudaStream_t s);
@@ -216,7 +236,8 @@ int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry
                      int use_lut, cudaStream_t s);
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
-                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s, int max_ctas = 0);
+                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s, int max_ctas = 0,
+                        bool pdl = false);
 size_t nws_mlp_tc_blob_floats();
 int nws_launch_mlp_tc_pack(NwsContext* ctx, const float* const* tensors, cudaStream_t s);
 int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, int T, int t_begin,
@@ -242,12 +263,14 @@ int nws_make_twiddle_master(NwsContext* ctx);
 // nws_mlp_small.cu
 bool nws_mlp_small_ok(const NwsContext* ctx, int B, int T);
 int nws_launch_mlp_small(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int B, int T, cudaStream_t s,
-                         const float2* xspec = nullptr, float* dry = nullptr, int hop_begin = 0, int hop_end = 0);
+                         const float2* xspec = nullptr, float* dry = nullptr, int hop_begin = 0, int hop_end = 0,
+                         bool pdl = false);
 // nws_reverb_direct.cu
 size_t nws_reverb_direct_scratch_bytes(int B, int N);
 bool nws_reverb_direct_ok(const NwsContext* ctx, int B, int N, size_t scratch_bytes);
-int nws_launch_reverb_direct(NwsContext* ctx, const float* x, float* out, float* scratch, int B, int N, cudaStream_t s);
+int nws_launch_reverb_direct(NwsContext* ctx, const float* x, float* out, float* scratch, int B, int N, cudaStream_t s,
+                             bool pdl = false);
 size_t nws_reverb_direct_causal_scratch_bytes(int B, int n_new_max);
 int nws_launch_reverb_direct_causal(NwsContext* ctx, const float* hist, const float* dry, size_t dry_stride, int first_sample,
                                     float* out, float* hist_next, float* scratch, int B, int n_new, int apply_reverb,
-                                    cudaStream_t s);
+                                    cudaStream_t s, bool pdl = false);

@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(kCluThreads, 1) nws_mlp_small_kernel(const Clu
       clu_cp4(Wo + k * kOutNoisePad + j, w + o.wt_out + (size_t)k * kBandsPad + rank * kOutNoise + j);
     }
   }
+  nws_pdl_wait();     // the front-end launch (GRU rows, noise spectrum) has completed ...
+  nws_pdl_launch();   // ... so the audio kernel may start its own prologue
   const float* rows = p.hbuf + (size_t)b * T * kEmb;
   for (int i = tid; i < T * kEmb / 4; i += kCluThreads) clu_cp16(reinterpret_cast<float4*>(X) + i, reinterpret_cast<const float4*>(rows) + i);
   clu_cp_wait_all();
@@ -273,7 +275,7 @@ bool nws_mlp_small_ok(const NwsContext* ctx, int B, int T) {
 }
 
 int nws_launch_mlp_small(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int B, int T, cudaStream_t s,
-                         const float2* xspec, float* dry, int hop_begin, int hop_end) {
+                         const float2* xspec, float* dry, int hop_begin, int hop_end, bool pdl) {
   CluParams p{};
   if (xspec && (hop_end - hop_begin > kClu * kNoiseHops || !dry)) { nws_set_error("nws_launch_mlp_small: bad fused noise range"); return NWS_ERR_INVALID; }
   p.xspec = xspec; p.tw_master = ctx->tw_master; p.dry = dry; p.hop_begin = hop_begin; p.hop_end = hop_end;
@@ -289,11 +291,11 @@ int nws_launch_mlp_small(const NwsContext* ctx, const float* hbuf, float* film, 
   cfg.blockDim = dim3(kCluThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kClu; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  int n_attr = 1;
+  nws_pdl_config(&cfg, attr, &n_attr, pdl);
   NWS_CUDA_OK(cudaLaunchKernelEx(&cfg, nws_mlp_small_kernel, p));
   NWS_LAUNCH_CHECK();
   return NWS_OK;

@@ -10,6 +10,46 @@ __device__ __forceinline__ void nws_load_tw256(float2* tw_s, const float2* __res
 }
 
 
+// X[t][k] = rfft(xp[128 t : 128 t + 256])[k], xp = reflect_pad(noise, 128)   (generators.py:31).
+// One CTA per pair of frames (all `nthreads` threads of the CTA must call).  `noise` null: the samples are this
+// forward's own draw (generators.py:30), generated in place from the Philox stream (seed, offset) exactly as
+// nws_rng_kernel would have written them.
+__device__ __forceinline__ float nws_noise_sample(const float* __restrict__ noise, int idx, uint64_t seed, uint64_t offset) {
+  if (noise) return noise[idx];
+  const NwsPhilox4 r = nws_philox4x32_10(offset + (uint64_t)(idx >> 2), 1ull, seed);
+  return nws_u32_to_unit(r.v[idx & 3]);
+}
+
+__device__ __forceinline__ void nws_noise_spectrum_body(int pair, int nthreads, const float* __restrict__ noise, int n_noise,
+                                                        uint64_t seed, uint64_t offset, const float2* __restrict__ tw_master,
+                                                        float2* __restrict__ xspec, int T) {
+  __shared__ float2 buf_a[256], buf_b[256], tw_s[128];
+  const int tid = threadIdx.x, ta = 2 * pair, tb = ta + 1;
+  nws_load_tw256(tw_s, tw_master, tid, nthreads);
+  for (int n = tid; n < 256; n += nthreads) {
+    float v[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int t = q == 0 ? ta : tb;
+      int idx = t * kHop + n - kIr / 2;               // index into the unpadded noise
+      if (idx < 0) idx = -idx;                        // reflect (no edge repeat)
+      if (idx >= n_noise) idx = 2 * (n_noise - 1) - idx;
+      v[q] = t < T ? nws_noise_sample(noise, idx, seed, offset) : 0.f;
+    }
+    buf_a[n] = make_float2(v[0], v[1]);
+  }
+  __syncthreads();
+  const float2* z = nws_fft_smem<false, false>(buf_a, buf_b, tw_s, 1, 8, 0, tid, nthreads);
+  for (int k = tid; k <= 128; k += nthreads) {
+    const float2 zk = z[k], zc = z[(256 - k) & 255];
+    // Xa = (Z[k] + conj(Z[N-k])) / 2 ; Xb = (Z[k] - conj(Z[N-k])) / (2i)
+    const float2 xa = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+    const float2 xb = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+    xspec[(size_t)ta * kBandsPad + k] = xa;
+    if (tb < T) xspec[(size_t)tb * kBandsPad + k] = xb;
+  }
+}
+
 // One CTA = one utterance x kNoiseHops output hops.  It filters frames t0-1 .. t0+kNoiseHops-1
 // (kNoiseHops+1 frames = (kNoiseHops+1)/2 complex FFTs, two at a time), keeps their 256-sample
 // outputs in shared memory and overlap-adds them into the kNoiseHops hops it owns.

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(kDirThreads) nws_reverb_direct_kernel(const Di
   const int tid = threadIdx.x, b = blockIdx.z, tq = tid & 63, grp = tid >> 6;
   const int n_blocks = (p.n_out + kDirOut - 1) / kDirOut;
   if ((int)blockIdx.x >= n_blocks) {
+    nws_pdl_wait();
     // history CTAs (streaming): hist_next[i] = input[NX - 32000 + i]
     const int n_hist_ctas = gridDim.x - n_blocks, c = blockIdx.x - n_blocks;
     if (blockIdx.y == 0 && p.hist_next)
@@ -71,8 +72,10 @@ __global__ void __launch_bounds__(kDirThreads) nws_reverb_direct_kernel(const Di
       }
       taps_s[q] = v;
     }
-    for (int q = tid; q < kDirIn; q += kDirThreads) x_s[q] = dir_input(p, b, j0 + q);
   }
+  nws_pdl_wait();   // the taps above are constants; the signal comes from the preceding launch
+  if (!p.dry_only)
+    for (int q = tid; q < kDirIn; q += kDirThreads) x_s[q] = dir_input(p, b, j0 + q);
   __syncthreads();
   // thread (tq, grp): outputs 4 tq .. 4 tq + 3, inputs 256 grp .. 256 grp + 255 of the tile
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -167,7 +170,19 @@ bool nws_reverb_direct_ok(const NwsContext* ctx, int B, int N, size_t scratch_by
   return scratch_bytes >= nws_reverb_direct_scratch_bytes(B, N);
 }
 
-int nws_launch_reverb_direct(NwsContext* ctx, const float* x, float* out, float* scratch, int B, int N, cudaStream_t s) {
+static int launch_direct(bool wrap, dim3 grid, const DirectParams& p, cudaStream_t s, bool pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kDirThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int n_attr = 0;
+  nws_pdl_config(&cfg, attr, &n_attr, pdl);
+  if (wrap) NWS_CUDA_OK(cudaLaunchKernelEx(&cfg, nws_reverb_direct_kernel<true>, p));
+  else NWS_CUDA_OK(cudaLaunchKernelEx(&cfg, nws_reverb_direct_kernel<false>, p));
+  NWS_LAUNCH_CHECK();
+  return NWS_OK;
+}
+
+int nws_launch_reverb_direct(NwsContext* ctx, const float* x, float* out, float* scratch, int B, int N, cudaStream_t s, bool pdl) {
   DirectParams p{};
   p.a = nullptr; p.a_stride = 0; p.len_a = 0;
   p.bsrc = x; p.b_stride = (size_t)N; p.b_off = 0; p.NX = N;
@@ -177,9 +192,7 @@ int nws_launch_reverb_direct(NwsContext* ctx, const float* x, float* out, float*
   p.S = (N + kDirIn - 1) / kDirIn;
   p.hist_next = nullptr;
   dim3 grid((N + kDirOut - 1) / kDirOut, p.S, B);
-  nws_reverb_direct_kernel<true><<<grid, kDirThreads, 0, s>>>(p);
-  NWS_LAUNCH_CHECK();
-  return NWS_OK;
+  return launch_direct(true, grid, p, s, pdl);
 }
 
 // ---- streaming causal form: input = [hist (32000) | dry_new (n_new)], outputs = the n_new new samples
@@ -190,7 +203,7 @@ size_t nws_reverb_direct_causal_scratch_bytes(int B, int n_new_max) {
 
 int nws_launch_reverb_direct_causal(NwsContext* ctx, const float* hist, const float* dry, size_t dry_stride, int first_sample,
                                     float* out, float* hist_next, float* scratch, int B, int n_new, int apply_reverb,
-                                    cudaStream_t s) {
+                                    cudaStream_t s, bool pdl) {
   DirectParams p{};
   p.a = hist; p.a_stride = kReverbIr; p.len_a = kReverbIr;
   p.bsrc = dry; p.b_stride = dry_stride; p.b_off = first_sample; p.NX = kReverbIr + n_new;
@@ -203,7 +216,5 @@ int nws_launch_reverb_direct_causal(NwsContext* ctx, const float* hist, const fl
   if ((long long)B * n_blocks > kDirCounters || B > 65535) { nws_set_error("reverb (direct): batch too large"); return NWS_ERR_UNSUPPORTED; }
   if (!apply_reverb) { p.S = 1; p.dry_only = 1; }   // dry output (and the history update) through the same launch
   dim3 grid(n_blocks + 4, p.S, B);   // + 4 history CTAs per utterance (blockIdx.y == 0 only)
-  nws_reverb_direct_kernel<false><<<grid, kDirThreads, 0, s>>>(p);
-  NWS_LAUNCH_CHECK();
-  return NWS_OK;
+  return launch_direct(false, grid, p, s, pdl);
 }

@@ -17,7 +17,9 @@
 // Every push re-runs the proven whole-utterance kernels on a short window [<= 3 history frames | new frames]
 // and renders only the hops whose neighbours are all real: hop h needs frame h+1 (second half of the hop
 // interpolates towards it), so the output lags the input by one hop until `flush`.
+#include "nws_hop_bodies.cuh"
 #include "nws_internal.cuh"
+#include "nws_noise_bodies.cuh"
 
 namespace {
 constexpr int kHist = 3;   // history frames kept: hop r0 >= 2 never sees the window's artificial left edge
@@ -32,9 +34,11 @@ struct NwsStreamState {
   bool flushed;
   uint64_t seed, offset;  // Philox stream of the noise draw (generators.py:30) when none is injected
   // device state
-  float* f0_h;        // [B][kHist]
-  float* ctrl_h;      // [B][2][kHist]
+  float* f0_h;        // [B][kHist]            } the current one of two copies each (hist_buf): the fused front-end launch
+  float* ctrl_h;      // [B][2][kHist]         } reads one while it writes the other
   float* hrow_h;      // [B][kHist][128] GRU outputs of the history frames
+  float* hist_buf[2][3];
+  int hist_cur;
   float* h_state;     // [B][128]
   double* phase_sum;  // [B]
   float* u_phase;     // [kHarmPad]
@@ -131,6 +135,86 @@ __global__ void __launch_bounds__(128) nws_stream_carry_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Front end of a short push in ONE launch (the streaming counterpart of nws_front_kernel): CTA roles by block index
+//   [0, B)     window assembly, the recurrence over the new frames and the next push's history, utterance b
+//   [B, 2B)    the fp64 phase carries of the rendered hops (continuing phase_sum), eight threads per hop
+//   [2B, ...)  one pair of noise frames each: the window's noise draw (Philox) and its spectrum
+// The history arrays are double-buffered (read `*_h`, write `*_h_next`): the carry CTAs read the old f0 history while
+// the window CTAs write the new one.
+struct NwsStreamFrontParams {
+  const float *w_hh, *w_ih, *b_ih, *b_hh;
+  const float *f0, *control; int C, Tn;                       // the push's new frames
+  const float *f0_h, *ctrl_h, *hrow_h; int n_hist;            // history in
+  float *f0_h_next, *ctrl_h_next, *hrow_h_next; int n_keep;   // history out
+  float *f0_w, *ctrl_w, *hbuf; int B, Tw;                     // window out
+  float* h_state;
+  double *carry, *phase_sum; int r0, r1;
+  const float* noise_in; uint64_t seed, offset; const float2* tw_master; float2* xspec;
+};
+
+__global__ void __launch_bounds__(kGates, 1) nws_stream_front_kernel(const NwsStreamFrontParams p) {
+  const int role = blockIdx.x, tid = threadIdx.x, Tw = p.Tw;
+  nws_pdl_launch();   // the MLP chain's weight prologue may start now (it waits for this grid before reading its results)
+  auto f0_at = [&](int b, int t) { return t < p.n_hist ? p.f0_h[b * kHist + t] : p.f0[(size_t)b * p.Tn + (t - p.n_hist)]; };
+  if (role < p.B) {
+    const int b = role;
+    for (int t = tid; t < Tw; t += kGates) {
+      float c0, c1;
+      if (t < p.n_hist) {
+        c0 = p.ctrl_h[(b * 2 + 0) * kHist + t];
+        c1 = p.ctrl_h[(b * 2 + 1) * kHist + t];
+      } else {
+        c0 = p.control[((size_t)b * p.C + 0) * p.Tn + (t - p.n_hist)];
+        c1 = p.control[((size_t)b * p.C + 1) * p.Tn + (t - p.n_hist)];
+      }
+      p.f0_w[(size_t)b * Tw + t] = f0_at(b, t);
+      p.ctrl_w[((size_t)b * 2 + 0) * Tw + t] = c0;
+      p.ctrl_w[((size_t)b * 2 + 1) * Tw + t] = c1;
+    }
+    for (int i = tid; i < p.n_hist * kEmb; i += kGates) p.hbuf[((size_t)b * Tw) * kEmb + i] = p.hrow_h[(size_t)b * kHist * kEmb + i];
+    __syncthreads();   // the window's control rows are read back by this same CTA
+    if (p.Tn > 0) nws_gru_body(b, p.w_hh, p.w_ih, p.b_ih, p.b_hh, p.ctrl_w, 2, p.hbuf, Tw, p.n_hist, Tw, p.h_state);
+    __syncthreads();
+    const int first = Tw - p.n_keep;
+    for (int i = tid; i < p.n_keep; i += kGates) {
+      p.f0_h_next[b * kHist + i] = p.f0_w[(size_t)b * Tw + first + i];
+      p.ctrl_h_next[(b * 2 + 0) * kHist + i] = p.ctrl_w[((size_t)b * 2 + 0) * Tw + first + i];
+      p.ctrl_h_next[(b * 2 + 1) * kHist + i] = p.ctrl_w[((size_t)b * 2 + 1) * Tw + first + i];
+    }
+    for (int i = tid; i < p.n_keep * kEmb; i += kGates)
+      p.hrow_h_next[(size_t)b * kHist * kEmb + i] = p.hbuf[((size_t)b * Tw + first) * kEmb + i];
+  } else if (role < 2 * p.B) {
+    __shared__ double hop_sum[kSmallMlpMaxFrames + 8];
+    const int b = role - p.B, t = p.r0 + (tid >> 3), part = tid & 7;
+    const float inv_hop = (float)Tw / (float)(Tw * kHop);
+    double s = 0.0;
+    if (t < p.r1) {
+      const float fm = f0_at(b, t > 0 ? t - 1 : 0), fc = f0_at(b, t), fp = f0_at(b, t + 1 < Tw ? t + 1 : Tw - 1);
+      for (int r = part * 16; r < part * 16 + 16; ++r) {
+        const NwsLerp c = nws_lerp_coords(t * kHop + r, Tw, inv_hop);
+        const float x0 = c.i0 == t ? fc : (c.i0 < t ? fm : fp);
+        const float x1 = c.i1 == t ? fc : (c.i1 < t ? fm : fp);
+        s += (double)nws_lerp_apply(c, x0, x1);
+      }
+    }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (t < p.r1 && part == 0) hop_sum[t - p.r0] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double run = p.phase_sum[b];
+      for (int i = p.r0; i < p.r1; ++i) {
+        p.carry[(size_t)b * Tw + i] = run;
+        run += hop_sum[i - p.r0];
+      }
+      p.phase_sum[b] = run;
+    }
+  } else {
+    nws_noise_spectrum_body(role - 2 * p.B, kGates, p.noise_in, kHop * Tw - 1, p.seed, p.offset, p.tw_master, p.xspec, Tw);
+  }
+}
+
 // reverb input window: [last 32000 dry samples | the hops rendered by this push]
 __global__ void nws_stream_assemble_kernel(const float* __restrict__ rev_hist, const float* __restrict__ dry_w, int Nw_dry,
                                            int first_sample, int n_new, float* __restrict__ xw) {
@@ -156,7 +240,9 @@ __global__ void nws_stream_finish_kernel(const float* __restrict__ xw, const flo
 
 extern "C" int nws_stream_destroy(NwsStreamHandle st) {
   if (!st) return NWS_OK;
-  cudaFree(st->f0_h); cudaFree(st->ctrl_h); cudaFree(st->hrow_h); cudaFree(st->h_state); cudaFree(st->phase_sum);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) cudaFree(st->hist_buf[i][j]);
+  cudaFree(st->h_state); cudaFree(st->phase_sum);
   cudaFree(st->u_phase); cudaFree(st->rev_hist_buf[0]); cudaFree(st->rev_hist_buf[1]); cudaFree(st->dir_scratch); cudaFree(st->f0_w); cudaFree(st->ctrl_w); cudaFree(st->noise_w);
   cudaFree(st->ws_base); cudaFree(st->xw); cudaFree(st->yw); cudaFree(st->rev_work);
   delete st;
@@ -176,9 +262,13 @@ extern "C" int nws_stream_create(NwsHandle ctx, int B, int max_frames, NwsStream
   st->rev_work_bytes = (size_t)((B + 1) / 2) * L * sizeof(float2);
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-  alloc((void**)&st->f0_h, (size_t)B * kHist * sizeof(float));
-  alloc((void**)&st->ctrl_h, (size_t)B * 2 * kHist * sizeof(float));
-  alloc((void**)&st->hrow_h, (size_t)B * kHist * kEmb * sizeof(float));
+  for (int i = 0; i < 2; ++i) {
+    alloc((void**)&st->hist_buf[i][0], (size_t)B * kHist * sizeof(float));
+    alloc((void**)&st->hist_buf[i][1], (size_t)B * 2 * kHist * sizeof(float));
+    alloc((void**)&st->hist_buf[i][2], (size_t)B * kHist * kEmb * sizeof(float));
+  }
+  st->hist_cur = 0;
+  st->f0_h = st->hist_buf[0][0]; st->ctrl_h = st->hist_buf[0][1]; st->hrow_h = st->hist_buf[0][2];
   alloc((void**)&st->h_state, (size_t)B * kEmb * sizeof(float));
   alloc((void**)&st->phase_sum, (size_t)B * sizeof(double));
   alloc((void**)&st->u_phase, kHarmPad * sizeof(float));
@@ -247,38 +337,59 @@ extern "C" int nws_stream_push(NwsStreamHandle st, const float* f0, const float*
   const NwsWorkspace w = nws_carve_workspace(st->ws_base, B, Tw, 256);
   const int M = B * Tw, Nw = Tw * kHop;
 
-  // window, encoder (new frames only; the recurrence continues from h_state), history for the next push
-  nws_stream_stage_in_kernel<<<B, 128, 0, s>>>(f0, control, ctrl_channels, n_frames, st->f0_h, st->ctrl_h, st->hrow_h, n_hist,
-                                               st->f0_w, st->ctrl_w, w.hbuf, Tw);
-  NWS_LAUNCH_CHECK();
-  if (n_frames > 0) NWS_TRY(nws_launch_gru(ctx, st->ctrl_w, 2, w.hbuf, B, Tw, n_hist, Tw, st->h_state, s));
   const int n_keep = Tw < kHist ? Tw : kHist;
-  nws_stream_stage_out_kernel<<<B, 128, 0, s>>>(st->f0_w, st->ctrl_w, w.hbuf, Tw, n_keep, st->f0_h, st->ctrl_h, st->hrow_h);
-  NWS_LAUNCH_CHECK();
+  const float* noise = noise_window;
+  // short pushes: window assembly, recurrence, history, phase carries, noise draw and spectrum in ONE launch
+  const bool fused = ctx->small_path && nws_front_ok(B, Tw) && nws_mlp_small_ok(ctx, B, Tw);
+  if (fused) {
+    NwsStreamFrontParams p{};
+    const float* wp = ctx->packed;
+    p.w_hh = wp + ctx->lay.gru_whh; p.w_ih = wp + ctx->lay.gru_wih; p.b_ih = wp + ctx->lay.gru_bih; p.b_hh = wp + ctx->lay.gru_bhh;
+    p.f0 = f0; p.control = control; p.C = ctrl_channels; p.Tn = n_frames;
+    p.f0_h = st->f0_h; p.ctrl_h = st->ctrl_h; p.hrow_h = st->hrow_h; p.n_hist = n_hist;
+    const int nx = st->hist_cur ^ 1;
+    p.f0_h_next = st->hist_buf[nx][0]; p.ctrl_h_next = st->hist_buf[nx][1]; p.hrow_h_next = st->hist_buf[nx][2]; p.n_keep = n_keep;
+    p.f0_w = st->f0_w; p.ctrl_w = st->ctrl_w; p.hbuf = w.hbuf; p.B = B; p.Tw = Tw;
+    p.h_state = st->h_state;
+    p.carry = w.carry; p.phase_sum = st->phase_sum; p.r0 = r0; p.r1 = n_out > 0 ? r1 : r0;
+    // noise[i] of the stream is Philox block (offset + i/4): the window starts at sample 128 * g_base
+    p.noise_in = noise; p.seed = st->seed; p.offset = st->offset + 32ull * (uint64_t)g_base;
+    p.tw_master = ctx->tw_master; p.xspec = w.xspec;
+    nws_stream_front_kernel<<<2 * B + (Tw + 1) / 2, kGates, 0, s>>>(p);
+    NWS_LAUNCH_CHECK();
+    st->hist_cur = nx;
+    st->f0_h = st->hist_buf[nx][0]; st->ctrl_h = st->hist_buf[nx][1]; st->hrow_h = st->hist_buf[nx][2];
+  } else {
+    // window, encoder (new frames only; the recurrence continues from h_state), history for the next push
+    nws_stream_stage_in_kernel<<<B, 128, 0, s>>>(f0, control, ctrl_channels, n_frames, st->f0_h, st->ctrl_h, st->hrow_h, n_hist,
+                                                 st->f0_w, st->ctrl_w, w.hbuf, Tw);
+    NWS_LAUNCH_CHECK();
+    if (n_frames > 0) NWS_TRY(nws_launch_gru(ctx, st->ctrl_w, 2, w.hbuf, B, Tw, n_hist, Tw, st->h_state, s));
+    nws_stream_stage_out_kernel<<<B, 128, 0, s>>>(st->f0_w, st->ctrl_w, w.hbuf, Tw, n_keep, st->f0_h, st->ctrl_h, st->hrow_h);
+    NWS_LAUNCH_CHECK();
+  }
   st->n_seen += n_frames;
   st->n_hist = n_keep;
   if (flush) st->flushed = true;
   if (n_out <= 0) return NWS_OK;
 
   // hop-rate chain over the window, then the rendered hops [r0, r1)
-  const float* noise = noise_window;
-  if (!noise) {
-    // noise[i] of the stream is Philox block (offset + i/4): the window starts at sample 128 * g_base
-    NWS_TRY(nws_launch_rng(nullptr, st->noise_w, Nw - 1, st->seed, st->offset + 32ull * (uint64_t)g_base, s));
-    noise = st->noise_w;
-  }
-  NWS_TRY(nws_launch_noise_spectrum(ctx, noise, w.xspec, Tw, s));
-  if (nws_mlp_small_ok(ctx, B, Tw)) {
-    // short pushes: cluster MLP chain with the noise filter fused (band gains stay in shared memory)
-    NWS_TRY(nws_launch_mlp_small(ctx, w.hbuf, w.film, nullptr, B, Tw, s, w.xspec, w.dry, r0, r1));
+  if (fused) {
+    // cluster MLP chain with the noise filter fused (band gains stay in shared memory)
+    NWS_TRY(nws_launch_mlp_small(ctx, w.hbuf, w.film, nullptr, B, Tw, s, w.xspec, w.dry, r0, r1, true));
   } else {
+    if (!noise) {
+      NWS_TRY(nws_launch_rng(nullptr, st->noise_w, Nw - 1, st->seed, st->offset + 32ull * (uint64_t)g_base, s));
+      noise = st->noise_w;
+    }
+    NWS_TRY(nws_launch_noise_spectrum(ctx, noise, w.xspec, Tw, s));
     NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, Tw, 0, Tw, s));
     NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, Tw, r0, r1, s));
+    nws_stream_carry_kernel<<<B, 128, (size_t)n_out * sizeof(double), s>>>(st->f0_w, w.carry, st->phase_sum, Tw, r0, r1);
+    NWS_LAUNCH_CHECK();
   }
-  nws_stream_carry_kernel<<<B, 128, (size_t)n_out * sizeof(double), s>>>(st->f0_w, w.carry, st->phase_sum, Tw, r0, r1);
-  NWS_LAUNCH_CHECK();
   NWS_TRY(nws_launch_audio_tc(ctx, st->f0_w, w.carry, w.film, st->u_phase, w.dry, w.dry, nullptr, B, Tw, r0, r1, ctx->tile_counters,
-                              use_lut, s));
+                              use_lut, s, 0, fused));
   st->n_rendered += n_out;
 
   // reverb as a causal convolution over [32000 past dry samples | new], keep the new part
@@ -287,7 +398,7 @@ extern "C" int nws_stream_push(NwsStreamHandle st, const float* f0, const float*
     // direct form: convolution, dry add and the history shift in ONE launch (nws_reverb_direct.cu)
     float* next = st->rev_hist == st->rev_hist_buf[0] ? st->rev_hist_buf[1] : st->rev_hist_buf[0];
     NWS_TRY(nws_launch_reverb_direct_causal(ctx, st->rev_hist, w.dry, (size_t)Nw, r0 * kHop, out, next, st->dir_scratch, B, n_new,
-                                            apply_reverb, s));
+                                            apply_reverb, s, fused));
     st->rev_hist = next;
     *n_out_frames = n_out;
     return NWS_OK;

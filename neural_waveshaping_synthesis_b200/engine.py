@@ -42,6 +42,7 @@ class NwsEngine:
             _lib.check(self.lib.nws_create(ctypes.byref(cfg), ctypes.byref(handle)))
         self.handle = handle
         self._ws: Optional[torch.Tensor] = None
+        self._ws_bytes = {}          # (B, T) -> workspace bytes (saves a library call per forward)
         self._keep = None          # tensors whose pointers the last load call used
         self.has_lut = False
         self.lut_shape = None
@@ -65,10 +66,14 @@ class NwsEngine:
         return self._ws
 
     def workspace_for(self, B: int, T: int) -> torch.Tensor:
-        n = self.lib.nws_workspace_bytes(self.handle, B, T)
-        if n == 0:
-            raise ValueError("unsupported shape B=%d T=%d" % (B, T))
-        return self._workspace(n)
+        n = self._ws_bytes.get((B, T))
+        if n is None:
+            n = self.lib.nws_workspace_bytes(self.handle, B, T)
+            if n == 0:
+                raise ValueError("unsupported shape B=%d T=%d" % (B, T))
+            self._ws_bytes[(B, T)] = n
+        ws = self._ws
+        return ws if ws is not None and ws.numel() >= n else self._workspace(n)
 
     def _next_rng(self, n_noise: int):
         """(seed, offset) of this forward's Philox draws, reserved on torch's CUDA generator exactly as
@@ -159,9 +164,15 @@ class NwsEngine:
             out = torch.empty(B, N, dtype=torch.float32, device=self.device)
         ws = self.workspace_for(B, T)
         seed, off = (0, 0) if (up is not None and nz is not None) else self._next_rng(N - 1)
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.nws_forward(self.handle, _ptr(f0c), _ptr(cc), cc.shape[1], _ptr(up), _ptr(nz), seed, off,
-                                            _ptr(out), B, T, 1 if use_lut else 0, _ptr(ws), ws.numel(), self._stream()))
+        if torch.cuda.current_device() == self.device.index:      # the common case: no device switch needed
+            rc = self.lib.nws_forward(self.handle, _ptr(f0c), _ptr(cc), cc.shape[1], _ptr(up), _ptr(nz), seed, off,
+                                      _ptr(out), B, T, 1 if use_lut else 0, _ptr(ws), ws.numel(), self._stream())
+        else:
+            with torch.cuda.device(self.device):
+                rc = self.lib.nws_forward(self.handle, _ptr(f0c), _ptr(cc), cc.shape[1], _ptr(up), _ptr(nz), seed, off,
+                                          _ptr(out), B, T, 1 if use_lut else 0, _ptr(ws), ws.numel(), self._stream())
+        if rc:
+            _lib.check(rc)
         return out
 
     def forward_host(self, f0: torch.Tensor, control: torch.Tensor, out: torch.Tensor, u_phase=None, noise=None,

@@ -61,6 +61,9 @@ class _PermissivePickle:
         return _PermissiveUnpickler(f, **kw).load()
 
 
+_GENERATION = __import__("itertools").count()
+
+
 def _version_of(t: torch.Tensor) -> int:
     """In-place modification counter of a tensor; tensors created under torch.inference_mode() do not track one
     (reading it raises): fall back to the pointer alone for those."""
@@ -149,16 +152,31 @@ class NeuralWaveshaping(nn.Module):
 
     def _weight_tensors(self):
         """The 49 tensors of the C ABI's NwsTensor order, cached per (module-structure) so the per-call
-        change check is 49 (data_ptr, version) reads instead of a state_dict() walk."""
+        change check is 49 version reads instead of a state_dict() walk."""
         key = (id(self.newt), id(self.newt._modules.get("shaping_fn")), id(self.embedding), id(self.reverb))
         cache = self.__dict__.get("_wt_cache")
         if cache is None or cache[0] != key:
             sd = self._state_for_engine()
-            cache = (key, sd, [sd[k] for k in _lib.TENSOR_KEYS])
+            cache = (key, sd, [sd[k] for k in _lib.TENSOR_KEYS], next(_GENERATION))
             object.__setattr__(self, "_wt_cache", cache)
         return cache[1], cache[2]
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() replace parameter storage without touching version counters
+        object.__setattr__(self, "_wt_cache", None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        object.__setattr__(self, "_wt_cache", None)
+        return super().load_state_dict(*args, **kwargs)
+
     def _engine_for(self, like: torch.Tensor) -> NwsEngine:
+        """The engine of the input's device with this module's current weights (and lookup table) loaded.
+
+        Called on every forward, so the up-to-date check is kept cheap (a 256-sample forward is ~35 us of GPU work):
+        sub-module identity (`model.newt = FastNEWT(model.newt)`), moves and casts (`_apply`), `load_state_dict`, and
+        in-place updates of any of the 49 tensors (their version counters) are noticed; re-pointing a single
+        parameter's `.data` at other storage is not — call `model.load_state_dict(model.state_dict())` after that."""
         dev = like.device
         if dev.type != "cuda":
             raise RuntimeError("NeuralWaveshaping (B200) runs on CUDA only: inputs are on %s. There is no CPU "
@@ -171,22 +189,25 @@ class NeuralWaveshaping(nn.Module):
                 if isinstance(m, BoundToRoot):
                     m._bind_root(self)
         sd, tensors = self._weight_tensors()
-        if tensors[0].device != dev:   # the module was moved since the tensor list was cached
-            object.__setattr__(self, "_wt_cache", None)
-            sd, tensors = self._weight_tensors()
-        sig = tuple([(t.data_ptr(), _version_of(t)) for t in tensors])
+        try:
+            vsum = sum([t._version for t in tensors])
+        except Exception:     # tensors created under torch.inference_mode() do not track versions
+            vsum = -1
+        fast = self.newt.lookup_table if isinstance(self.newt, FastNEWT) else None
         tag = self._loaded.get(dev)
-        if tag is None or tag[0] != sig:
+        key = (self._wt_cache[3], vsum)      # (generation of the tensor list, sum of the in-place version counters)
+        if tag is None or tag[0] != key:
+            if tensors[0].device != dev:
+                raise RuntimeError("the model's parameters are on %s but the inputs are on %s" % (tensors[0].device, dev))
             for m in self.modules():
                 if isinstance(m, BoundToRoot):
                     m._bind_root(self)
             eng.load_weights(sd)
-            tag = (sig, None)
-        if isinstance(self.newt, FastNEWT):
-            t = self.newt.lookup_table
-            lsig = (t.data_ptr(), _version_of(t), self.newt.table_min, self.newt.table_max)
+            tag = (key, None)
+        if fast is not None:
+            lsig = (fast.data_ptr(), _version_of(fast), self.newt.table_min, self.newt.table_max)
             if tag[1] != lsig:
-                eng.set_lut(t, self.newt.table_min, self.newt.table_max)
+                eng.set_lut(fast, self.newt.table_min, self.newt.table_max)
                 tag = (tag[0], lsig)
         self._loaded[dev] = tag
         return eng

@@ -31,6 +31,17 @@ def main():
                 for k, v in eng.stage_times_ms().items():
                     acc[k] = acc.get(k, 0.0) + v / 20
             eng.set_profiling(False)
+            import time
+            for rep in range(2):
+                evs = []
+                t0 = time.perf_counter()
+                for _ in range(100):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); model(f0, control); b.record(); evs.append((a, b))
+                host = (time.perf_counter() - t0) / 100
+                torch.cuda.synchronize()
+                ts = sorted(a.elapsed_time(b) for a, b in evs)
+                print("bs %d eager median %.1f us, host time per call %.1f us" % (bs, ts[50] * 1e3, host * 1e6), flush=True)
             u_g, nz_g = torch.rand(101, device=dev), torch.rand(128 * T - 1, device=dev)
             model(f0, control, phase_shift=u_g, noise=nz_g)
             torch.cuda.synchronize()

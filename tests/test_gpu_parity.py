@@ -632,6 +632,7 @@ def _run_stream(m, f0, control, u, noise, chunks, reverb):
     ("randinit", False, [4, 1, 3, 2]),             # ragged pushes, single-frame push
     ("vn", True, [8, 8]),
     ("vn", False, [5, 11]),
+    ("vn", True, [50, 3, 45]),                     # pushes beyond the short-push kernels: tile MLP chain, FFT reverb
 ])
 def test_stream_equals_whole_utterance(tag, fast, chunks):
     """Chunked synthesis == the whole-utterance forward (dry), and == dry * causal reverb (wet)."""
