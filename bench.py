@@ -373,7 +373,6 @@ def config_c4(args, cpu_model, dev, flush):
                      "`graph_replay` = the forward captured once into a CUDA graph (no per-call host work ahead of the first kernel)",
            "sizes": BUFFER_SIZES, "stream_sizes": STREAM_SIZES}
     iters = 40
-    sweep = golden_case  # noqa: F841
     for variant in ("fastnewt", "newt"):
         model = copy.deepcopy(cpu_model)
         if variant == "fastnewt":

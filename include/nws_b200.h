@@ -13,7 +13,14 @@
  *   - `stream` is a cudaStream_t (CUstream) passed as void*; all work is enqueued on it and the
  *     calls do not synchronise the host unless stated;
  *   - return value 0 = NWS_OK, negative = error (nws_last_error() gives a thread-local message);
- *   - a handle may be used from one thread at a time.
+ *   - a handle may be used from one thread and on one stream at a time: its internal streams, events, scheduler
+ *     counters and the packed weights are per handle, so a forward must not overlap another forward or a
+ *     nws_load_weights / nws_set_lut of the same handle issued on a different stream (create one handle per stream);
+ *   - the tensor-core kernels wait on their mbarriers with a bound: if one ever gives up it writes NaNs and raises a
+ *     sticky flag that every later entry point of the handle reports as NWS_ERR_CUDA (see nws_status);
+ *   - limits: T >= 2 frames (the reference's reflect padding has the same limit) and 128*T + 31999 <= 2^20 samples
+ *     (about 63.5 s at 16 kHz: the largest reverb transform built); longer inputs return NWS_ERR_UNSUPPORTED — split
+ *     them or use the streaming entry points (nws_stream_*), whose reverb is causal.
  */
 #ifndef NWS_B200_H_
 #define NWS_B200_H_
