@@ -208,6 +208,13 @@ int nws_stage_control_to_params(NwsHandle handle, const float* control, int ctrl
  * batch is large enough (B*T >= 4096, T >= 129).  0 = strictly serial kernels on the caller's stream. */
 int nws_set_pipeline(NwsHandle handle, int enable);
 
+/* Implementation of the GRU recurrence (ControlModule, neural_waveshaping.py:17-26): 1 (default) = tensor cores from 64
+ * utterances on — eight utterances per CTA as the N of a warp-level mma m16n8k16, W_hh resident in registers as
+ * fp16-split fragments with fp32-equivalent products (csrc/nws_gru_mma.cu) — and fp32 SIMT, one utterance per CTA, below
+ * (csrc/nws_hop_bodies.cuh: the shorter step while the chip is not full; also inside the fused short-buffer front end
+ * and the streaming path); 0 = fp32 SIMT always; 2 = tensor cores for any batch (cross-checks).                  */
+int nws_set_gru_impl(NwsHandle handle, int impl);
+
 /* Implementation of the hop-rate MLP chain: 1 (default) = one tcgen05 kernel, activations in TMEM, weights
  * streamed by cp.async.bulk (csrc/nws_mlp_tc.cu); 0 = fp32 SIMT layer kernels (csrc/nws_encoder.cu). */
 int nws_set_mlp_impl(NwsHandle handle, int impl);
@@ -216,6 +223,14 @@ int nws_set_mlp_impl(NwsHandle handle, int impl);
  * the accumulator in TMEM (csrc/nws_audio_tc.cu), 0 = fp32 SIMT (csrc/nws_audio.cu, kept as the
  * in-library cross-check). */
 int nws_set_audio_impl(NwsHandle handle, int impl);
+/* Where the filtered-noise branch (FIRNoiseSynth.forward, generators.py:21-35) of a whole-utterance forward runs:
+ * 0 (default) = nws_noise_filter_kernel writes the filtered noise into the output buffer first and the fused audio-rate
+ * kernel adds its samples to it; 1 = inside the fused audio-rate kernel: the warpgroup's MMA-issuing warp filters the
+ * next tile's hop while the compute warps run the current tile's epilogue (band gains and noise spectrum straight from
+ * L2, one in-place 256-point inverse FFT per frame pair in shared memory, overlap-add in registers; nothing of the branch
+ * touches HBM).  Both are parity-tested against each other and the oracle; the in-kernel variant is the slower one on
+ * B200 (FastNEWT audio kernel 0.514 -> 0.575 ms against 0.049 ms for the separate launch), hence not the default.   */
+int nws_set_noise_fused(NwsHandle handle, int enable);
 /* How the fused kernel evaluates the NEWT shapers' two 8x8 hidden layers (TrainableNonlinearity, shaping.py:25-34):
  * 1 (default) = on the tensor cores (warp-level mma m16n8k8, 3xTF32), 0 = fp32 FMA with the weights shared by lane
  * pairs.  Both are parity-tested; the switch exists for cross-checks and measurements.                        */

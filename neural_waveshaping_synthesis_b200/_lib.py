@@ -112,6 +112,10 @@ def load_library():
         L.nws_set_reverb_direct.restype = c_int
         L.nws_set_shaper_impl.argtypes = [vp, c_int]
         L.nws_set_shaper_impl.restype = c_int
+        L.nws_set_gru_impl.argtypes = [vp, c_int]
+        L.nws_set_gru_impl.restype = c_int
+        L.nws_set_noise_fused.argtypes = [vp, c_int]
+        L.nws_set_noise_fused.restype = c_int
         L.nws_selftest_umma.argtypes = [vp, vp, vp, c_int, c_int, vp, vp]
         L.nws_selftest_umma.restype = c_int
         L.nws_set_profiling.argtypes = [vp, c_int]
@@ -164,7 +168,7 @@ EXPORTED_SYMBOLS = [
     "nws_stream_create", "nws_stream_destroy", "nws_stream_reset", "nws_stream_window", "nws_stream_push",
     "nws_loudness_workspace_bytes", "nws_extract_loudness", "nws_extract_rms", "nws_selftest_ffma_peak",
     "nws_tensor_numel", "nws_status", "nws_interp_frames_len", "nws_interp_frames",
-    "nws_set_shaper_impl", "nws_set_reverb_direct", "nws_set_small_path",
+    "nws_set_shaper_impl", "nws_set_reverb_direct", "nws_set_small_path", "nws_set_gru_impl", "nws_set_noise_fused",
 ]
 
 # Shapes the kernels are built for (gin/models/newt.gin) in TENSOR_KEYS order.  The C side reads

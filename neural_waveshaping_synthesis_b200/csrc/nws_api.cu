@@ -58,9 +58,10 @@ extern "C" int nws_create(const NwsConfig* cfg, NwsHandle* out) {
   e = cudaHostAlloc((void**)&ctx->fault_host, sizeof(int), cudaHostAllocMapped);
   if (e == cudaSuccess) { *ctx->fault_host = 0; e = cudaHostGetDevicePointer((void**)&ctx->fault_dev, ctx->fault_host, 0); }
   if (e != cudaSuccess) { nws_set_error("nws_create: %s", cudaGetErrorString(e)); nws_destroy(ctx); return NWS_ERR_CUDA; }
-  e = cudaMalloc(&ctx->dir_counters, (kDirCounters + 4) * sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(ctx->dir_counters, 0, (kDirCounters + 4) * sizeof(int));
+  e = cudaMalloc(&ctx->dir_counters, (kDirCounters + 4 + kMaxTimeBlocks) * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->dir_counters, 0, (kDirCounters + 4 + kMaxTimeBlocks) * sizeof(int));
   ctx->tile_counters = ctx->dir_counters ? ctx->dir_counters + kDirCounters : nullptr;
+  ctx->gru_done = ctx->dir_counters ? ctx->dir_counters + kDirCounters + 4 : nullptr;
   if (e != cudaSuccess) { nws_set_error("nws_create: %s", cudaGetErrorString(e)); nws_destroy(ctx); return NWS_ERR_CUDA; }
   int rc = nws_make_twiddle_master(ctx);
   if (rc) { nws_destroy(ctx); return rc; }
@@ -72,6 +73,7 @@ extern "C" int nws_create(const NwsConfig* cfg, NwsHandle* out) {
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   for (int i = 0; i < kMaxTimeBlocks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_block[i], cudaEventDisableTiming);
+  for (int i = 0; i < kMaxTimeBlocks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_mlp[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_early_ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_early_done, cudaEventDisableTiming);
@@ -90,8 +92,10 @@ extern "C" int nws_destroy(NwsHandle ctx) {
   if (ctx->ev_early_ready) cudaEventDestroy(ctx->ev_early_ready);
   if (ctx->ev_early_done) cudaEventDestroy(ctx->ev_early_done);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  for (int i = 0; i < kMaxTimeBlocks; ++i)
+  for (int i = 0; i < kMaxTimeBlocks; ++i) {
     if (ctx->ev_block[i]) cudaEventDestroy(ctx->ev_block[i]);
+    if (ctx->ev_mlp[i]) cudaEventDestroy(ctx->ev_mlp[i]);
+  }
   cudaFree(ctx->packed);
   cudaFree(ctx->mlp_tc);
   cudaFree(ctx->lut);
@@ -182,6 +186,21 @@ extern "C" int nws_load_weights(NwsHandle ctx, const float* const* tensors, int 
   if (rc) return rc;
   rc = nws_launch_mlp_tc_pack(ctx, tensors, s);
   if (rc) return rc;
+  {
+    // the tensor-core recurrence splits W_hh into fp16 pairs: every weight must be finite and inside the fp16 range
+    // (trained values are O(1)); otherwise the fp32 kernel is used
+    float* hw = (float*)malloc((size_t)kGates * kEmb * sizeof(float));
+    if (!hw) { nws_set_error("nws_load_weights: out of host memory"); return NWS_ERR_CUDA; }
+    cudaError_t e = cudaMemcpyAsync(hw, tensors[NWS_T_GRU_W_HH], (size_t)kGates * kEmb * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { free(hw); nws_set_error("nws_load_weights: %s", cudaGetErrorString(e)); return NWS_ERR_CUDA; }
+    bool ok = true;
+    for (int i = 0; i < kGates * kEmb; ++i) ok = ok && fabsf(hw[i]) <= 32768.0f;   // (false for NaN)
+    free(hw);
+    ctx->gru_mma_ok = ok;
+    rc = nws_launch_pack_gru_mma(ctx, tensors[NWS_T_GRU_W_HH], s);
+    if (rc) return rc;
+  }
   ctx->weights_loaded = true;
   ctx->lut_valid = false;
   nws_reverb_invalidate(ctx);
@@ -372,6 +391,18 @@ extern "C" int nws_set_reverb_direct(NwsHandle ctx, int enable) {
   return NWS_OK;
 }
 
+extern "C" int nws_set_gru_impl(NwsHandle ctx, int impl) {
+  if (!ctx || impl < 0 || impl > 2) { nws_set_error("nws_set_gru_impl: impl must be 0 (fp32 SIMT recurrence), 1 (tensor cores from 64 utterances on) or 2 (tensor cores always)"); return NWS_ERR_INVALID; }
+  ctx->gru_impl = impl;
+  return NWS_OK;
+}
+
+extern "C" int nws_set_noise_fused(NwsHandle ctx, int enable) {
+  if (!ctx) { nws_set_error("nws_set_noise_fused: NULL handle"); return NWS_ERR_INVALID; }
+  ctx->noise_fused = enable != 0;
+  return NWS_OK;
+}
+
 extern "C" int nws_set_shaper_impl(NwsHandle ctx, int impl) {
   if (!ctx || (impl != 0 && impl != 1)) { nws_set_error("nws_set_shaper_impl: impl must be 0 (fp32 FMA layers) or 1 (tensor-core 8x8 layers)"); return NWS_ERR_INVALID; }
   ctx->shaper_impl = impl;
@@ -437,28 +468,61 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   const int M = B * T, N = T * kHop;
 
   const int n_blocks = (T + 127) / 128;
-  const int gru_ctas = B;   // SMs the recurrence occupies (one utterance per CTA)
+  const int gru_ctas = nws_gru_ctas(ctx, B);   // SMs the recurrence occupies
   const bool pipelined = ctx->pipeline && ctx->mlp_impl && ctx->audio_impl && !ctx->profile && ctx->enc_stream &&
                          ctx->aux_stream && n_blocks >= 3 && (long long)B * T >= 4096 && gru_ctas + 16 <= ctx->sm_count;
-  const int t_split = 128, early_end = t_split - 1;   // pipelined: hops [0,127) only need FiLM frames 0..127
+  // Time blocks of the pipelined order.  fp32 recurrence (B SMs for ~0.7 us per step): a 128-frame head, then the rest.
+  // Tensor-core recurrence (B/8 SMs, ~1.15 us per step): equal blocks of `pipe_block` frames — the rest of the chip
+  // renders block k while the encoder's SMs produce block k+1.
+  int tb[kMaxTimeBlocks + 1] = {0}, nb = 0;
+  const bool gru_mma = gru_ctas != B;
+  bool gru_marks = false;   // one encoder launch with progress marks (below)
   if (pipelined) {
-    // The GRU is T dependent steps on B SMs; everything downstream only needs the frames already encoded.
-    // The recurrence is cut after 128 frames: while the encoder stream runs the remaining steps, the head
-    // block goes through the MLP chain and the noise branch and its audio hops are rendered on the SMs the
-    // GRU does not occupy (persistent CTAs, capped; tiles claimed dynamically).  Stream/event dependencies only.
+    if (!gru_mma) { tb[1] = 128; tb[2] = T; nb = 2; }
+    else {
+      static const int blk_env = getenv("NWS_PIPE_BLOCK") ? atoi(getenv("NWS_PIPE_BLOCK")) : 0;   // development switches
+      static const int first_env = getenv("NWS_PIPE_FIRST") ? atoi(getenv("NWS_PIPE_FIRST")) : 0;
+      const int blk = blk_env >= 16 ? blk_env : ctx->pipe_block, first = first_env >= 2 ? first_env : ctx->pipe_first;
+      nb = 1 + (T - first + blk / 2) / blk;   // a short remainder joins the last block
+      if (nb < 2) nb = 2;
+      if (nb > kMaxTimeBlocks) nb = kMaxTimeBlocks;
+      for (int k = 1; k < nb; ++k) tb[k] = first + (k - 1) * blk;
+      tb[nb] = T;
+    }
+    // The GRU is T dependent steps on a few SMs; everything downstream only needs the frames already encoded.  The
+    // recurrence runs on an internal high-priority stream; the blocks already encoded go through the MLP chain and the
+    // noise branch and their audio hops are rendered on the SMs the GRU does not occupy (persistent CTAs, capped; tiles
+    // claimed dynamically).  fp32 recurrence: one launch per block (hidden state carried in `h_state`), stream events.
+    // Tensor-core recurrence: ONE launch that never gives up its SMs — a relaunch per block lost them to the waiting
+    // MLP CTAs for 30 us each time — and counts its CTAs past each block boundary in `gru_done`; the consumers' streams
+    // wait for the count with a one-thread kernel.
     // The encoder only reads `control`, so it is forked first: the draws, phase carries and noise spectrum
     // below run beside its first steps instead of ahead of them.
     cudaStream_t g = ctx->enc_stream;
     g_tl.on = getenv("NWS_TIMELINE") != nullptr;
     g_tl.mark("fork", s);
+    // (inside a stream capture the per-block launches and events are kept: a graph does not promise that the waiting
+    // kernel and the encoder run concurrently)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NWS_CUDA_OK(cudaStreamIsCapturing(s, &cap));
+    gru_marks = gru_mma && cap == cudaStreamCaptureStatusNone;
+    if (gru_marks) NWS_CUDA_OK(cudaMemsetAsync(ctx->gru_done, 0, kMaxTimeBlocks * sizeof(int), s));
     NWS_CUDA_OK(cudaEventRecord(ctx->ev_fork, s));
     NWS_CUDA_OK(cudaStreamWaitEvent(g, ctx->ev_fork, 0));
-    NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, t_split, w.h_state, g));
-    NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[0], g));
-    g_tl.mark("gru head", g);
-    NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, t_split, T, w.h_state, g));
-    NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[1], g));
-    g_tl.mark("gru rest", g);
+    if (gru_marks) {
+      NwsGruMarks marks;
+      marks.n = nb;
+      for (int k = 0; k < nb; ++k) marks.t[k] = tb[k + 1];
+      NWS_TRY(nws_launch_gru_mma(ctx, control, ctrl_channels, w.hbuf, B, T, 0, T, nullptr, g, ctx->gru_done, &marks));
+      NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[0], g));   // (joins the encoder stream back into the caller's at the end)
+      g_tl.mark("gru", g);
+    } else {
+      for (int k = 0; k < nb; ++k) {
+        NWS_TRY(nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, tb[k], tb[k + 1], w.h_state, g));
+        NWS_CUDA_OK(cudaEventRecord(ctx->ev_block[k], g));
+        g_tl.mark("gru block", g);
+      }
+    }
   }
 
   // Short buffers (the sweep of scripts/time_buffer_sizes.py: 2..32 frames): latency is launches, not work.  One launch
@@ -497,28 +561,32 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
   g_tl.mark("draws+carry+spec", s);
 
   if (pipelined) {
+    // block k's chain (MLP -> noise hops -> audio hops) alternates between the caller's stream and the auxiliary one,
+    // the last block on the caller's: consecutive audio launches overlap at their tails (separate tile counters)
     cudaStream_t aux = ctx->aux_stream;
-    // caller's stream: head block -> early audio on the auxiliary stream, on the SMs the GRU leaves free
-    NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[0], 0));
-    NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, 0, t_split, s));
-    NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, 0, t_split, s));
-    g_tl.mark("mlp+noise head", s);
     NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_ready, s));
     NWS_CUDA_OK(cudaStreamWaitEvent(aux, ctx->ev_early_ready, 0));
-    NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, 0, early_end, ctx->tile_counters + 2,
-                                use_lut, aux, ctx->sm_count - gru_ctas));
-    NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_done, aux));
-    g_tl.mark("audio head", aux);
-    // the rest, once everything is encoded; its audio overlaps the tail of the early launch
-    NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[1], 0));
-    NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, t_split, T, s));
-    g_tl.mark("mlp rest", s);
-    NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, t_split, T, s));
-    g_tl.mark("noise rest", s);
-    NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, early_end, T,
-                                ctx->tile_counters, use_lut, s));
-    g_tl.mark("audio rest", s);
-    NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_early_done, 0));
+    bool aux_used = false;
+    for (int k = 0; k < nb; ++k) {
+      const bool last = k == nb - 1, on_aux = ((nb - 1 - k) & 1) != 0;
+      cudaStream_t c = on_aux ? aux : s;
+      if (gru_marks) NWS_TRY(nws_launch_wait_counter(ctx->gru_done + k, gru_ctas, c));
+      else NWS_CUDA_OK(cudaStreamWaitEvent(c, ctx->ev_block[k], 0));
+      if (k > 0) NWS_CUDA_OK(cudaStreamWaitEvent(c, ctx->ev_mlp[k - 1], 0));   // frames tb[k]-2, tb[k]-1 of the block before
+      NWS_TRY(nws_launch_mlp_tc(ctx, w.hbuf, w.film, w.bands, M, T, tb[k], tb[k + 1], c));
+      NWS_CUDA_OK(cudaEventRecord(ctx->ev_mlp[k], c));
+      // hop h blends towards frame h + 1: the block's last frame waits for the next block
+      const int hb = k == 0 ? 0 : tb[k] - 1, he = last ? T : tb[k + 1] - 1;
+      // the noise branch: inside the audio kernel (default), or its own launch writing into `dry` first
+      if (!ctx->noise_fused) NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, hb, he, c));
+      NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, ctx->noise_fused ? nullptr : w.dry, w.dry, nullptr, B, T, hb, he,
+                                  ctx->tile_counters + (on_aux ? 2 : 0), use_lut, c, last ? 0 : ctx->sm_count - gru_ctas, false,
+                                  ctx->noise_fused ? w.bands : nullptr, w.xspec));
+      g_tl.mark(on_aux ? "block chain (aux)" : "block chain", c);
+      if (on_aux) { NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_done, aux)); aux_used = true; }
+    }
+    if (aux_used) NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_early_done, 0));
+    if (gru_marks) NWS_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_block[0], 0));
   } else {
     NWS_STAGE(ctx, kStGru, s, nws_launch_gru(ctx, control, ctrl_channels, w.hbuf, B, T, 0, T, nullptr, s));
     if (ctx->mlp_impl && nws_mlp_small_ok(ctx, B, T)) {
@@ -533,10 +601,15 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
       NWS_STAGE(ctx, kStMlpFilm, s, nws_launch_td_mlp(ctx, NWS_MLP_FILM, w.emb, w.act0, w.act1, w.film, M, s));
       NWS_STAGE(ctx, kStMlpNoise, s, nws_launch_td_mlp(ctx, NWS_MLP_NOISE, w.emb, w.act0, w.act1, w.bands, M, s));
     }
-    // noise branch -> dry
-    NWS_STAGE(ctx, kStNoiseFilter, s, nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, 0, T, s));
-    // fused audio-rate kernel: dry = newt(exciter) + noise
-    NWS_STAGE(ctx, kStAudio, s, launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, ctx->tile_counters, use_lut, s));
+    if (ctx->noise_fused && ctx->audio_impl) {
+      // fused audio-rate kernel, noise branch included: dry = newt(exciter) + filtered noise
+      NWS_STAGE(ctx, kStAudio, s, nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, nullptr, w.dry, nullptr, B, T, 0, T,
+                                                      ctx->tile_counters, use_lut, s, 0, false, w.bands, w.xspec));
+    } else {
+      // noise branch -> dry, then the fused audio-rate kernel: dry = newt(exciter) + noise
+      NWS_STAGE(ctx, kStNoiseFilter, s, nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, 0, T, s));
+      NWS_STAGE(ctx, kStAudio, s, launch_audio(ctx, f0, w.carry, w.film, u_phase, w.dry, w.dry, nullptr, B, T, ctx->tile_counters, use_lut, s));
+    }
   }
   // reverb: direct form for short buffers (one launch instead of three 32000-point passes), FFT otherwise
   const size_t rev_bytes = (size_t)((B + 1) / 2) * nws_reverb_fft_len(N) * sizeof(float2);

@@ -30,6 +30,11 @@ struct NwsAudioParams {
   int lut_size;
   float lut_min, lut_span, lut_span_rcp;
   const float* noise_in;  // [B][N] or null: added to the mixdown (neural_waveshaping.py:85-86)
+  // Noise branch inside the kernel (nws_audio_tc.cu; `noise_in` is ignored then): the band gains of the noise MLP,
+  // the spectrum of the shared noise vector and the twiddle table — FIRNoiseSynth.forward, generators.py:21-35
+  const float* bands;     // [B*T][kBandsPad] frame-major, or null
+  const float2* xspec;    // [T][kBandsPad]
+  const float2* tw_master;// [kTwMaster / 2]
   float* out;             // [B][N]
   float* exciter_out;     // [B][64][N] or null
   int B, T;

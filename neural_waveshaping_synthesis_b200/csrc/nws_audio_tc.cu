@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "nws_audio_common.cuh"
+#include "nws_fft.cuh"
 #include "nws_tc.cuh"
 
 // Oscillator sine: NWS_OSC_FAST=1 selects the SFU version (3.6e-7 max abs error on B200 instead of
@@ -101,8 +102,171 @@ struct TcCfg {
   static constexpr int oCoef = oFilm + kWgs * 3 * kFilm * 4;     // [wg][half][64][8] floats: FiLM lerp coefficients
   static constexpr int oSmall = oCoef + kWgs * 2 * kShapers * 8 * 4;  // (hmix_b, mix_w)[64] | shift[104] | input_scale[64] floats
   static constexpr int oShaper = oSmall + (kShapers + kHarmPad + kShapers + kShapers) * 4;
-  static constexpr int kBytes = oShaper + (USE_LUT ? 0 : kShapers * kShpTcStride * 4);   // (kShpTcStride >= kShaperStride)
+  static constexpr int oNoise = oShaper + (USE_LUT ? 0 : kShapers * kShpTcStride * 4);   // (kShpTcStride >= kShaperStride)
+  // noise branch: twiddles [128] float2 | per warpgroup: the frame pair's spectrum / transform [256] float2 (in place) |
+  // finished noise samples of this tile and the next [2][128]
+  static constexpr int kNoiseWg = 256 * 8 + 2 * 128 * 4;
+  static constexpr int kBytes = oNoise + 128 * 8 + kWgs * kNoiseWg;
 };
+
+// ---- Filtered-noise branch inside the fused kernel (FIRNoiseSynth.forward, generators.py:21-35; the identities of
+// nws_noise.cu): the frame's response is real — (-1)^k (0.5 H[k] + 0.25 (H[k-1] + H[k+1])) — so filtering is a bin-wise
+// product with the shared noise spectrum, and two real frames (fa in the real part, fa + 1 in the imaginary part) come
+// back through ONE 256-point complex inverse FFT.  The work is done by the warpgroup's MMA-issuing warp while the
+// compute warps are in the tile's epilogue (half of a tile's time, during which that warp has nothing to issue): it
+// filters the NEXT tile's hop — a single warp, so the transform needs no CTA barrier (in-place radix-4 decimation in
+// frequency, __syncwarp between passes, digit-reversed read-out) — and the compute warps never execute an instruction
+// of the noise branch.  (Slicing the transform between the stages' MMA issues instead delayed those issues — a lone
+// warp runs ~150 dependent instructions per slice at its own latency — and cost the kernel 14 %.)
+struct NwsNoiseRegs {
+  float4 ha, hb;          // band gains 4 lane .. 4 lane + 3 of frames fa, fa + 1
+  float ha128, hb128;     // ... and the Nyquist band
+  float4 xa[2], xb[2];    // noise spectrum bins 4 lane .. 4 lane + 3 (re, im interleaved)
+  float2 xa128, xb128;
+};
+
+__device__ __forceinline__ void nws_noise_fetch(NwsNoiseRegs& r, const float* __restrict__ bands_b, const float2* __restrict__ xspec,
+                                                int fa, bool va, bool vb, int lane) {
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.ha = r.hb = z4; r.xa[0] = r.xa[1] = r.xb[0] = r.xb[1] = z4;
+  r.ha128 = r.hb128 = 0.f; r.xa128 = r.xb128 = make_float2(0.f, 0.f);
+  if (va) {
+    const float* h = bands_b + (size_t)fa * kBandsPad;
+    const float2* x = xspec + (size_t)fa * kBandsPad;
+    r.ha = *reinterpret_cast<const float4*>(h + 4 * lane); r.ha128 = h[128];
+    r.xa[0] = *reinterpret_cast<const float4*>(x + 4 * lane); r.xa[1] = *reinterpret_cast<const float4*>(x + 4 * lane + 2);
+    r.xa128 = x[128];
+  }
+  if (vb) {
+    const float* h = bands_b + (size_t)(fa + 1) * kBandsPad;
+    const float2* x = xspec + (size_t)(fa + 1) * kBandsPad;
+    r.hb = *reinterpret_cast<const float4*>(h + 4 * lane); r.hb128 = h[128];
+    r.xb[0] = *reinterpret_cast<const float4*>(x + 4 * lane); r.xb[1] = *reinterpret_cast<const float4*>(x + 4 * lane + 2);
+    r.xb128 = x[128];
+  }
+}
+
+// slice 0: Z[k] = Ya[k] + i Yb[k], Y = X * Hw, Hermitian-extended to 256 bins, natural order
+__device__ __forceinline__ void nws_noise_spectrum_slice(float2* zb, const NwsNoiseRegs& r, int lane) {
+  auto put = [&](int kk, float hwa, float hwb, float2 xa, float2 xb) {
+    float2 ya = make_float2(xa.x * hwa, xa.y * hwa), yb = make_float2(xb.x * hwb, xb.y * hwb);
+    if (kk == 0 || kk == 128) { ya.y = 0.f; yb.y = 0.f; }   // irfft ignores the imaginary part of DC / Nyquist
+    zb[kk] = make_float2(ya.x - yb.y, ya.y + yb.x);
+    if (kk > 0 && kk < 128) zb[256 - kk] = make_float2(ya.x + yb.y, yb.x - ya.y);   // conj(Ya) + i conj(Yb)
+  };
+  // neighbours across lanes: band 4 lane - 1 (lane 0: band 1 mirrors), band 4 lane + 4 (lane 31: band 128)
+  float la = __shfl_up_sync(0xffffffffu, r.ha.w, 1), lb = __shfl_up_sync(0xffffffffu, r.hb.w, 1);
+  float ra = __shfl_down_sync(0xffffffffu, r.ha.x, 1), rb = __shfl_down_sync(0xffffffffu, r.hb.x, 1);
+  const float a127 = __shfl_sync(0xffffffffu, r.ha.w, 31), b127 = __shfl_sync(0xffffffffu, r.hb.w, 31);
+  if (lane == 0) { la = r.ha.y; lb = r.hb.y; }
+  if (lane == 31) { ra = r.ha128; rb = r.hb128; }
+  const float ha[6] = {la, r.ha.x, r.ha.y, r.ha.z, r.ha.w, ra}, hb[6] = {lb, r.hb.x, r.hb.y, r.hb.z, r.hb.w, rb};
+  const float2 xa[4] = {make_float2(r.xa[0].x, r.xa[0].y), make_float2(r.xa[0].z, r.xa[0].w), make_float2(r.xa[1].x, r.xa[1].y), make_float2(r.xa[1].z, r.xa[1].w)};
+  const float2 xb[4] = {make_float2(r.xb[0].x, r.xb[0].y), make_float2(r.xb[0].z, r.xb[0].w), make_float2(r.xb[1].x, r.xb[1].y), make_float2(r.xb[1].z, r.xb[1].w)};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float sgn = (j & 1) ? -1.f : 1.f;   // (-1)^kk, kk = 4 lane + j
+    put(4 * lane + j, sgn * fmaf(0.25f, ha[j] + ha[j + 2], 0.5f * ha[j + 1]), sgn * fmaf(0.25f, hb[j] + hb[j + 2], 0.5f * hb[j + 1]), xa[j], xb[j]);
+  }
+  if (lane == 0)   // Nyquist: both neighbours are band 127
+    put(128, fmaf(0.25f, a127 + a127, 0.5f * r.ha128), fmaf(0.25f, b127 + b127, 0.5f * r.hb128), r.xa128, r.xb128);
+}
+
+// slices 1..4: pass `s` (0..3) of the in-place radix-4 decimation-in-frequency inverse transform; block length
+// L = 256 >> 2s, two butterflies per lane.  X[4k' + m] of a block = (sum_r x[n' + r L/4] i^(r m)) W_L^(n' m), stored at
+// block position m L/4 + n'; the final element order is the base-4 digit reversal.
+__device__ __forceinline__ void nws_noise_fft_pass(float2* zb, const float2* tw_s, int s, int lane) {
+  const int log_q = 6 - 2 * s, q = 1 << log_q;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = lane + 32 * u, pos = j & (q - 1), base = ((j >> log_q) << (log_q + 2)) + pos;
+    float2 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[r] = zb[base + r * q];
+    const float2 a0 = nws_cadd(v[0], v[2]), a1 = nws_csub(v[0], v[2]), a2 = nws_cadd(v[1], v[3]), d = nws_csub(v[1], v[3]);
+    const float2 a3 = make_float2(-d.y, d.x);   // * (+i)
+    float2 o[4] = {nws_cadd(a0, a2), nws_cadd(a1, a3), nws_csub(a0, a2), nws_csub(a1, a3)};
+    if (s < 3 && pos) {
+#pragma unroll
+      for (int m = 1; m < 4; ++m) o[m] = nws_cmul(o[m], nws_twiddle<true>(tw_s, 1, (pos * m) << (2 * s), 128));   // W_L^(pos m) = W_256^(pos m 256/L)
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) zb[base + m * q] = o[m];
+  }
+}
+
+// slice 5: read-out (digit reversal), scale, overlap-add.  Lane holds samples lane + 32 i (i < 4) of a hop; `keep` = second
+// half of the newest frame (registers).  mode 0: frames (t-1, t) -> this hop (istft's envelope is 1 in the first hop, 2
+// elsewhere); mode 1: frames (t, t+1) -> this hop from the kept tail and the next hop, finished ahead; mode 2: only the
+// tail of the pair's second frame is wanted.
+__device__ __forceinline__ void nws_noise_output_slice(const float2* zb, float* out_now, float (&out_next)[4], float (&keep)[4],
+                                                       int mode, bool first_hop, int lane) {
+  auto rev = [](int n) { return ((n & 3) << 6) | ((n & 12) << 2) | ((n & 48) >> 2) | ((n & 192) >> 6); };
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = lane + 32 * i;
+    const float2 lo = zb[rev(n)], hi = zb[rev(128 + n)];
+    const float a_first = lo.x * (1.0f / 256.0f), a_second = hi.x * (1.0f / 256.0f);
+    const float b_first = lo.y * (1.0f / 256.0f), b_second = hi.y * (1.0f / 256.0f);
+    if (mode == 1) {
+      out_now[n] = 0.5f * (keep[i] + a_first);
+      out_next[i] = 0.5f * (a_second + b_first);
+    } else if (mode == 0) {
+      out_now[n] = first_hop ? b_first : 0.5f * (a_second + b_first);
+    }
+    keep[i] = b_second;
+  }
+}
+
+// Noise state of one MMA warp.  keep[] = second half of frame t_kept of utterance u (this lane's four samples per hop);
+// hold[] = the finished samples of hop `next` (or next = -1).  Frames are always paired as (2m - 1, 2m), whoever
+// transforms them, so the samples do not depend on how tiles were handed out (repeat runs are bit-identical): an even
+// hop t needs the pair (t-1, t); an odd hop needs the tail of (t-2, t-1) — kept from the hop before when the warpgroup
+// rendered it, else transformed for its tail alone — and the pair (t, t+1), which also finishes hop t+1.  A chunk of
+// consecutive hops costs one transform per two hops plus one or two at its start.
+struct NwsNoiseWarp {
+  const float* bands;      // [B*T][kBandsPad]
+  const float2* xspec;     // [T][kBandsPad]
+  const float2* tw;        // shared memory, [128]
+  float2* z;               // shared memory, [256]
+  int T, flim;             // frames from flim on are not needed (and may not be encoded yet)
+  int u, t_kept, next;
+  float keep[4], hold[4];
+};
+
+// The filtered-noise samples of hop t of utterance b -> out[128] (shared memory), then one arrival on `bar`.
+__device__ __noinline__ void nws_noise_tile(NwsNoiseWarp& c, int b, int t, float* out, uint64_t* bar) {
+  const int lane = threadIdx.x & 31;
+  if (c.u == b && c.next == t) {   // finished by the previous transform
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[lane + 32 * i] = c.hold[i];
+    c.next = -1;
+  } else {
+    const bool odd = t & 1, kept = c.u == b && c.t_kept == t - 1;
+    const float* bands_b = c.bands + (size_t)b * c.T * kBandsPad;
+    const int n_tr = odd && !kept ? 2 : 1;
+    for (int k = 0; k < n_tr; ++k) {
+      const bool last = k == n_tr - 1;
+      const int fa = !last ? t - 2 : (odd ? t : t - 1);
+      NwsNoiseRegs r;
+      nws_noise_fetch(r, bands_b, c.xspec, fa, fa >= 0 && fa < c.flim, fa + 1 < c.flim, lane);
+      nws_noise_spectrum_slice(c.z, r, lane);
+      __syncwarp();
+#pragma unroll 1
+      for (int s = 0; s < 4; ++s) {
+        nws_noise_fft_pass(c.z, c.tw, s, lane);
+        __syncwarp();
+      }
+      nws_noise_output_slice(c.z, out, c.hold, c.keep, !last ? 2 : (odd ? 1 : 0), t == 0, lane);
+      __syncwarp();
+    }
+    c.u = b;
+    c.t_kept = odd ? t + 1 : t;
+    c.next = odd ? t + 1 : -1;
+  }
+  __syncwarp();
+  if (lane == 0) nws_mbar_arrive(bar);   // (release: the warp's stores above are ordered before it)
+}
 
 __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 // Stage-operand-written barrier of (warpgroup, stage buffer): named barriers 5..12, 128 producer threads arrive
@@ -177,6 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   using C = TcCfg<USE_LUT>;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t free_bar[kWgs][2];   // the MMAs that read the stage have completed (tcgen05.commit)
+  __shared__ uint64_t nz_bar[kWgs][2];     // the filtered-noise samples of a tile are in its slot of shared memory (slots and barriers alternate per tile)
   __shared__ double warp_tot[kWgs + 1][4];
   __shared__ float2 film_k[kWgs][4];       // per (warpgroup, warp): partial sums of w_c*(Ab_n, Db_n) over the warp's 32 channels
   __shared__ uint32_t tmem_base_s;
@@ -220,12 +385,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       dst[5] = make_float4(r[kShpW4 + 2 * t], r[kShpW4 + 2 * t + 1], r[kShpB4], 0.f);
     }
   }
+  // noise branch (p.bands): twiddles of the 256-point transform; per warpgroup the transform buffer and the finished
+  // samples of this tile / the next one (written by the MMA warp, read by the compute threads at the end of the tile)
+  float2* nz_tw = reinterpret_cast<float2*>(smem + C::oNoise);
+  unsigned char* nz_wg = smem + C::oNoise + 128 * 8;   // (per-warpgroup areas, kNoiseWg bytes each)
+  const bool nz_on = p.bands != nullptr;
+  if (nz_on && tid < 128) nz_tw[tid] = p.tw_master[tid * (kTwMaster / 256)];
   if (tid < kWgs) done_s[tid] = 0;
   if (tid < 32) nws_tmem_alloc(&tmem_base_s, C::kTmemColsWg * kWgs);
   if (tid == 0) {
     for (int i = 0; i < kWgs * 2; ++i) {
       nws_mbar_init(&free_bar[0][0] + i, 1);
     }
+    for (int i = 0; i < kWgs * 2; ++i) nws_mbar_init(&nz_bar[0][0] + i, 1);
     nws_fence_mbar_init();
   }
   nws_fence_proxy_async();   // the weight tiles were written through the generic proxy
@@ -263,6 +435,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     const uint32_t acc = __shfl_sync(0xffffffffu, tmem_base_s, 0) + w * C::kTmemColsWg;
     const uint64_t dbh0 = nws_umma_smem_desc(w_hi_addr, kLboB, kSbo), dbl0 = nws_umma_smem_desc(w_lo_addr, kLboB, kSbo);
     const bool issuer = nws_elect_one();
+    NwsNoiseWarp nzc;
+    nzc.bands = p.bands; nzc.xspec = p.xspec; nzc.tw = nz_tw; nzc.z = reinterpret_cast<float2*>(nz_wg + w * C::kNoiseWg);
+    nzc.T = T; nzc.flim = p.t_end < T ? p.t_end : T; nzc.u = -1; nzc.t_kept = -2; nzc.next = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { nzc.keep[i] = 0.f; nzc.hold[i] = 0.f; }
+    float* nz_out_w = reinterpret_cast<float*>(nzc.z + 256);
+    int mpar = 0;
+    bool nz_first = nz_on;
+    auto nz_tile = [&](int slot) {   // the noise of the tile published in tile_s[w][slot], if there is one
+      const int tl = tile_s[w][slot];
+      if (tl >= n_tiles) return;
+      int q = (int)__umulhi((uint32_t)tl, hops_magic), r = tl - q * hops;
+      if (r >= hops) { ++q; r -= hops; }
+      nws_noise_tile(nzc, q, p.t_begin + r, nz_out_w + slot * 128, &nz_bar[w][slot]);
+    };
     for (;;) {   // one iteration per tile of warpgroup w; tiles are handed out dynamically
       fill_wait(w, 0);
       if (done_s[w]) break;   // woken by the warpgroup running out of tiles
@@ -286,7 +473,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
           nws_umma_commit(&free_bar[w][buf]);
         }
         __syncwarp();
+        // the warpgroup's very first tile: nobody filtered its noise ahead (the one delay of a stage issue per CTA)
+        if (st == 0 && nz_first) { nz_tile(mpar); nz_first = false; }
       }
+      // Every stage of this tile is issued; the compute warps now wait for the accumulator and run the epilogue: the
+      // time to filter the noise of the NEXT tile (its index was published when this one started; its slot and barrier
+      // are the other pair, last read at the end of the tile before this one).
+      if (nz_on) nz_tile(mpar ^ 1);
+      mpar ^= 1;
     }
   } else
   {
@@ -335,6 +529,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   int tile = tile_s[wg][0];
   if (tile < n_tiles) film_prefetch(tile);
   int par = 0;
+  const float* nz_out = reinterpret_cast<const float*>(nz_wg + wg * C::kNoiseWg + 256 * 8);
+  uint32_t nz_phase = 0;
   for (;;) {
     if (tile >= n_tiles) break;
     if (wt == 0) {
@@ -496,7 +692,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     }
     }
     // the noise-branch sample that is added to the mixdown at the very end: its latency hides behind the shaper loop
-    const float noise_v = p.noise_in ? __ldcs(p.noise_in + (size_t)b * N + n) : 0.f;   // (aliases p.out: not the read-only path; streaming: read once, keep L1 for the table)
+    // the noise-branch sample that is added to the mixdown at the very end: its latency hides behind the shaper loop
+    const float noise_in_v = (!nz_on && p.noise_in) ? __ldcs(p.noise_in + (size_t)b * N + n) : 0.f;   // (aliases p.out: not the read-only path; streaming: read once, keep L1 for the table)
     {  // accumulator complete when the last stage's commit lands (a commit covers all earlier MMAs)
       const int lb = (C::NST - 1) & 1;
       const uint32_t u = lb ? uses1 : uses0;
@@ -631,6 +828,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     }
     nws_tc_fence_before();   // TMEM reads ordered before the next tile's first MMA (via the warpgroup barrier)
     float o = fmaf(l1, mix_d + mix_kd, mix_a + mix_ka) + mix_b;
+    float noise_v = noise_in_v;
+    if (nz_on) {   // filtered by the MMA warp during the previous tile's epilogue (long done: one try_wait)
+      if (ok) ok = nws_mbar_wait(&nz_bar[wg][par], (nz_phase >> par) & 1u);
+      nz_phase ^= 1u << par;
+      noise_v = nz_out[par * 128 + wt];
+    }
     o += noise_v;
     p.out[(size_t)b * N + n] = ok ? o : __int_as_float(0x7fc00000);
     tile = tile_next;
@@ -675,8 +878,10 @@ int launch_variant(const NwsAudioParams& p, const float* wu, int* fault, int gri
 
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
-                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s, int max_ctas, bool pdl) {
+                        int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s, int max_ctas, bool pdl,
+                        const float* bands, const float2* xspec) {
   NwsAudioParams p{};
+  p.bands = bands; p.xspec = xspec; p.tw_master = ctx->tw_master;
   const float* w = ctx->packed;
   p.f0 = f0; p.carry = carry; p.film = film; p.u_phase = u_phase;
   p.hmix_wt = w + ctx->lay.hmix_wt; p.hmix_b = w + ctx->lay.hmix_b; p.rand_phase = w + ctx->lay.rand_phase;

@@ -27,8 +27,21 @@ nws_gru_kernel(const float* __restrict__ w_hh, const float* __restrict__ w_ih, c
   nws_gru_body(blockIdx.x, w_hh, w_ih, b_ih, b_hh, control, ctrl_channels, hbuf, T, t_begin, t_end, h_state);
 }
 
+// Which recurrence encodes B utterances.  The fp32 kernel steps faster (0.70 us against 1.15 us: the legacy HMMA pipe
+// is the tensor-core kernel's bound) but takes one SM per utterance; the tensor-core kernel takes one SM per EIGHT.
+// Measured on B200 (scripts/dev_pipe.py): equal at 64 utterances x 4 s (0.99 ms per FastNEWT forward either way, NEWT
+// 2.93 against 2.97 ms), 13 % faster at 256 (3.04 against 3.50 ms: the fp32 kernel needs two waves there and leaves no
+// SMs to pipeline with); below 64 the chip is not full and the shorter step wins.  gru_impl 2 forces it for any B.
+constexpr int kGruMmaMinBatch = 64;
+static bool nws_gru_uses_mma(const NwsContext* ctx, int B) {
+  return ctx->gru_mma_ok && (ctx->gru_impl == 2 || (ctx->gru_impl == 1 && B >= kGruMmaMinBatch));
+}
+
+int nws_gru_ctas(const NwsContext* ctx, int B) { return nws_gru_uses_mma(ctx, B) ? nws_gru_mma_ctas(B) : B; }
+
 int nws_launch_gru(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, int B, int T,
                    int t_begin, int t_end, float* h_state, cudaStream_t s) {
+  if (nws_gru_uses_mma(ctx, B)) return nws_launch_gru_mma(ctx, control, ctrl_channels, hbuf, B, T, t_begin, t_end, h_state, s);
   const float* p = ctx->packed;
   nws_gru_kernel<<<B, kGates, 0, s>>>(p + ctx->lay.gru_whh, p + ctx->lay.gru_wih, p + ctx->lay.gru_bih,
                                       p + ctx->lay.gru_bhh, control, ctrl_channels, hbuf, T, t_begin, t_end, h_state);

@@ -23,11 +23,11 @@ __device__ __forceinline__ float2 nws_twiddle(const float2* __restrict__ tw, int
 // `n_fft` = 1 << log_nfft independent FFTs of length N = 1 << log_n (every count is a power of two, so all index
 // arithmetic is shifts and masks — runtime integer divisions made these kernels instruction-bound).  Element e of FFT f lives at buf[e * n_fft + f] when
 // INTERLEAVED (consecutive threads -> consecutive FFTs: conflict-free for column transforms), else at
-// buf[f * N + e].  All threads of the CTA must call; ping-pongs between a and b and returns the buffer
-// holding the natural-order result.
-template <bool INVERSE, bool INTERLEAVED>
-__device__ __forceinline__ float2* nws_fft_smem(float2* a, float2* b, const float2* __restrict__ tw, int tw_stride,
-                                                int log_n, int log_nfft, int tid, int n_threads) {
+// buf[f * N + e].  All `n_threads` threads of the group must call (`sync` is the group's barrier: the CTA's, or a
+// warpgroup's named barrier); ping-pongs between a and b and returns the buffer holding the natural-order result.
+template <bool INVERSE, bool INTERLEAVED, class Sync>
+__device__ __forceinline__ float2* nws_fft_smem_sync(float2* a, float2* b, const float2* __restrict__ tw, int tw_stride,
+                                                     int log_n, int log_nfft, int tid, int n_threads, Sync sync) {
   const int N = 1 << log_n, half = N >> 1, n_fft = 1 << log_nfft;
   int ns = 1, s = 0;
   while (s < log_n) {
@@ -71,8 +71,14 @@ __device__ __forceinline__ float2* nws_fft_smem(float2* a, float2* b, const floa
       ns <<= 1;
       s += 1;
     }
-    __syncthreads();
+    sync();
     float2* t = a; a = b; b = t;
   }
   return a;
+}
+
+template <bool INVERSE, bool INTERLEAVED>
+__device__ __forceinline__ float2* nws_fft_smem(float2* a, float2* b, const float2* __restrict__ tw, int tw_stride,
+                                                int log_n, int log_nfft, int tid, int n_threads) {
+  return nws_fft_smem_sync<INVERSE, INTERLEAVED>(a, b, tw, tw_stride, log_n, log_nfft, tid, n_threads, [] { __syncthreads(); });
 }

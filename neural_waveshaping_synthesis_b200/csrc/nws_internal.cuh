@@ -38,6 +38,7 @@ struct NwsTdMlpOffsets {
 
 struct NwsPackedLayout {
   int gru_whh, gru_wih, gru_bih, gru_bhh;
+  int gru_mma;                     // W_hh as fp16-split mma.m16n8k16 A fragments in per-thread register order (nws_gru_mma.cu)
   int proj_wt, proj_b;
   NwsTdMlpOffsets mlp[2];
   int hmix_wt, hmix_b;             // [kHarmPad][64] k-major, [64]
@@ -57,6 +58,7 @@ inline NwsPackedLayout nws_packed_layout() {
   L.gru_wih = take(kGates * 2);
   L.gru_bih = take(kGates);
   L.gru_bhh = take(kGates);
+  L.gru_mma = take(kGates * kEmb);
   L.proj_wt = take(kEmb * kEmb);
   L.proj_b = take(kEmb);
   for (int m = 0; m < 2; ++m) {
@@ -115,12 +117,16 @@ struct NwsContext {
   float* mlp_tc = nullptr;     // TC weight blob (hi/lo parts, canonical UMMA layout, chunked)
   int mlp_tc_off[11] = {};
   float shaper_inner_bound = 1e30f;   // max_j(|b_j| + sum_i |W_ji|) over shaper layers 2-4 (set by nws_load_weights)
+  int gru_impl = 1;            // 1 = tensor-core recurrence (8 utterances per CTA, nws_gru_mma.cu) from 64 utterances on, 0 = fp32 SIMT always, 2 = tensor cores always
+  bool gru_mma_ok = false;     // W_hh finite and inside the fp16 range (checked by nws_load_weights)
+  int noise_fused = 0;         // whole-utterance forward: 1 = the FIR noise branch runs inside nws_audio_tc_kernel (its MMA warps), 0 = nws_noise_filter_kernel first (measured faster: DESIGN.md)
   int audio_impl = 1;          // 1 = tcgen05 harmonic mixer (nws_audio_tc.cu), 0 = fp32 SIMT (nws_audio.cu)
   int shaper_impl = 1;         // NEWT shaper layers inside nws_audio_tc_kernel: 1 = mma.sync 8x8 layers, 0 = fp32 FMA (paired lanes)
   int device = 0;
   // mbarrier-timeout flag of the tcgen05 kernels: one int in mapped pinned host memory (the kernels write it
   // only on a timeout; every API call reads the host side without a synchronise and fails with NWS_ERR_CUDA)
   int* tile_counters = nullptr; // [4] = two {tiles claimed, CTAs done} pairs of nws_audio_tc_kernel's scheduler (main / early launch)
+  int* gru_done = nullptr;     // [kMaxTimeBlocks] CTAs of the tensor-core recurrence that have passed each progress mark (zeroed per forward)
   int* dir_counters = nullptr; // [kDirCounters] zero between launches (nws_reverb_direct.cu)
   int small_path = 1;          // few frames: 1 = fp32 small-batch MLP chain (nws_mlp_small.cu), 0 = always the 128-frame-tile kernel
   int reverb_direct = 1;       // short buffers: 1 = direct-form reverb, 0 = always the FFT path
@@ -131,7 +137,9 @@ struct NwsContext {
   int pipeline = 1;
   cudaStream_t enc_stream = nullptr, aux_stream = nullptr;
   cudaEvent_t ev_early_ready = nullptr, ev_early_done = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_block[kMaxTimeBlocks] = {};
+  cudaEvent_t ev_fork = nullptr, ev_block[kMaxTimeBlocks] = {}, ev_mlp[kMaxTimeBlocks] = {};
+  int pipe_first = 32;         // ... and of the first block (the chip idles until it is encoded)
+  int pipe_block = 117;        // frames per time block when the tensor-core recurrence encodes (nws_forward)
   // optional per-stage timing of nws_forward (cudaEvents on the launch stream)
   bool profile = false;
   cudaEvent_t ev[2 * 10] = {};
@@ -223,6 +231,16 @@ inline void nws_pdl_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, i
 int nws_launch_phase_carry(const float* f0, double* carry, int B, int T, cudaStream_t s);
 int nws_launch_gru(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, int B, int T,
                    int t_begin, int t_end, float* h_state, cudaStream_t s);
+// nws_gru_mma.cu
+int nws_gru_ctas(const NwsContext* ctx, int B);   // CTAs (= SMs) the recurrence of B utterances occupies
+int nws_gru_mma_ctas(int B);
+int nws_launch_pack_gru_mma(NwsContext* ctx, const float* w_hh, cudaStream_t s);
+// progress marks of one nws_gru_mma_kernel launch: after frame t[k] - 1 every CTA adds one to done[k]
+struct NwsGruMarks { int n = 0; int t[kMaxTimeBlocks] = {}; };
+int nws_launch_gru_mma(const NwsContext* ctx, const float* control, int ctrl_channels, float* hbuf, int B, int T,
+                       int t_begin, int t_end, float* h_state, cudaStream_t s, int* done = nullptr,
+                       const NwsGruMarks* marks = nullptr);
+int nws_launch_wait_counter(const int* counter, int target, cudaStream_t s);
 int nws_launch_linear(const float* X, const float* Wt, const float* bias, const float* ln_g, const float* ln_b,
                       float* Y, int M, int n_out, int ldw, int ldy, bool ln_act, cudaStream_t s);
 int nws_launch_td_mlp(const NwsContext* ctx, int which, const float* emb, float* act0, float* act1, float* out,
@@ -237,7 +255,7 @@ int nws_launch_audio(const NwsContext* ctx, const float* f0, const double* carry
 int nws_launch_audio_tc(const NwsContext* ctx, const float* f0, const double* carry, const float* film,
                         const float* u_phase, const float* noise_in, float* out, float* exciter_out, int B, int T,
                         int t_begin, int t_end, int* tile_counter, int use_lut, cudaStream_t s, int max_ctas = 0,
-                        bool pdl = false);
+                        bool pdl = false, const float* bands = nullptr, const float2* xspec = nullptr);
 size_t nws_mlp_tc_blob_floats();
 int nws_launch_mlp_tc_pack(NwsContext* ctx, const float* const* tensors, cudaStream_t s);
 int nws_launch_mlp_tc(const NwsContext* ctx, const float* hbuf, float* film, float* bands, int M, int T, int t_begin,

@@ -48,6 +48,10 @@ __device__ __host__ __forceinline__ uint32_t nws_umma_idesc_tf32(int M, int N) {
 __device__ __forceinline__ void nws_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nws_smem_u32(bar)), "r"(count) : "memory");
 }
+// one arrival (release at CTA scope: the thread's earlier shared-memory stores are visible to whoever observes the phase)
+__device__ __forceinline__ void nws_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nws_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void nws_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ uint32_t nws_mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

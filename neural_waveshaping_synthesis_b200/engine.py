@@ -205,6 +205,15 @@ class NwsEngine:
         """NEWT shaper hidden layers: 1 = tensor cores (mma.sync, default), 0 = fp32 FMA (paired lanes)."""
         _lib.check(self.lib.nws_set_shaper_impl(self.handle, impl))
 
+    def set_noise_fused(self, enable: bool):
+        """Filtered-noise branch as its own launch ahead of the fused audio kernel (default, faster) or inside it."""
+        _lib.check(self.lib.nws_set_noise_fused(self.handle, 1 if enable else 0))
+
+    def set_gru_impl(self, impl: int):
+        """GRU recurrence: 1 = tensor cores (8 utterances per CTA) from 64 utterances on, fp32 SIMT below (default);
+        0 = fp32 SIMT always; 2 = tensor cores always."""
+        _lib.check(self.lib.nws_set_gru_impl(self.handle, impl))
+
     def set_pipeline(self, enable: bool):
         """Pipelined forward (GRU time blocks on an internal stream overlapped with rendering); default on."""
         _lib.check(self.lib.nws_set_pipeline(self.handle, 1 if enable else 0))

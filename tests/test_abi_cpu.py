@@ -168,6 +168,8 @@ int use_abi(void* stream) {
   nws_set_mlp_impl(h, 1);
   nws_set_audio_impl(h, 1);
   nws_set_shaper_impl(h, 1);
+  nws_set_gru_impl(h, 1);
+  nws_set_noise_fused(h, 1);
   nws_set_reverb_direct(h, 1);
   nws_set_small_path(h, 1);
   nws_selftest_umma(0, 0, 0, 8, 0, 0, stream);

@@ -59,6 +59,36 @@ def test_control_embedding(tag, eng_rand, eng_vn):
     assert err(emb, lit)[0] < (2e-5 if tag == "randinit" else 1e-3)
 
 
+@pytest.mark.parametrize("B", [1, 5, 8, 13])
+@pytest.mark.parametrize("tag", ["randinit", "vn"])
+def test_gru_tensor_core_vs_oracle(tag, B, eng_rand, eng_vn):
+    """The tensor-core recurrence (csrc/nws_gru_mma.cu: eight utterances per CTA, fp16-split operands, forced here for
+    any batch by nws_set_gru_impl(2)) against the oracle's step loop and against the fp32 kernel — ragged batches
+    (dead MMA columns), odd frame counts."""
+    eng, w = eng_rand if tag == "randinit" else eng_vn
+    T = 75
+    gen = torch.Generator().manual_seed(100 + B)
+    if tag == "vn":
+        _, c1 = oracle.realistic_inputs(T, w["data_mean"].numpy(), w["data_std"].numpy(), B=1)
+        control = (c1 * (1.0 + 0.05 * torch.randn(B, 1, 1, generator=gen)) + 0.02 * torch.randn(B, 2, T, generator=gen)).contiguous()
+    else:
+        control = torch.rand(B, 2, T, generator=gen)
+    lit = oracle.gru_literal(w, control)
+    lit = torch.nn.functional.conv1d(lit.transpose(1, 2), w["embedding.proj.weight"], w["embedding.proj.bias"])
+    try:
+        eng.set_gru_impl(2)
+        emb_tc = eng.control_embedding(control.cuda())
+        eng.set_gru_impl(0)
+        emb_fp32 = eng.control_embedding(control.cuda())
+    finally:
+        eng.set_gru_impl(1)
+    tol = 2e-5 if tag == "randinit" else 1e-3   # (recurrent amplification on the trained weights: see test_control_embedding)
+    assert err(emb_tc, lit)[0] < tol, err(emb_tc, lit)
+    assert err(emb_tc, emb_fp32)[0] < tol, err(emb_tc, emb_fp32)
+    if tag == "randinit":
+        assert err(emb_tc, emb_fp32)[0] < 1e-6
+
+
 @pytest.mark.parametrize("tag", ["randinit", "vn"])
 def test_td_mlps(tag, eng_rand, eng_vn):
     eng, w = eng_rand if tag == "randinit" else eng_vn
@@ -326,11 +356,19 @@ def test_full_size_batch_properties():
         y2 = m(f0b.cuda(), cb.cuda(), **args)
         assert torch.equal(y1, y2)
         assert torch.isfinite(y1).all()
+        eng = m._engine_for(f0b.cuda())
         for i in (0, 17, 63):
+            # the batch of 64 is encoded by the tensor-core recurrence, a single utterance by the fp32 one unless told
+            # otherwise: same kernel -> fp32 round-off; the other kernel -> the checkpoint tolerance (App. A.6)
+            eng.set_gru_impl(2)
             yi = m(f0b[i:i + 1].cuda(), cb[i:i + 1].cuda(), **args)
+            eng.set_gru_impl(1)
             # not bit-equal by design: the reverb transforms two utterances per complex FFT (real/imaginary
             # parts), so the partner utterance perturbs the rounding — values agree to fp32 round-off
             assert err(yi[0], y1[i])[0] < 2e-6 * float(y1[i].abs().max()), i
+            yf = m(f0b[i:i + 1].cuda(), cb[i:i + 1].cuda(), **args)
+            e = err(yf[0], y1[i])
+            assert e[0] < TOL_CKPT_MAX and e[1] < TOL_CKPT_RMS, (i, e)
         ref = oracle.forward(w, f0b[63:64], cb[63:64], u, noise, lut=oracle.build_lookup_table(w))
     e = err(y1[63:64], ref)
     assert e[0] < TOL_CKPT_MAX and e[1] < TOL_CKPT_RMS, e
@@ -549,7 +587,8 @@ def test_pipelined_forward_equals_serial():
     """The pipelined forward (GRU time blocks on an internal stream, rendering overlapped) runs the same
     arithmetic as the serial one — equal to fp32 round-off (the noise branch pairs frames differently in its
     two-for-one FFTs when hops are rendered block by block), deterministic, including a ragged last block."""
-    for tag, fast, B, T in (("vn", True, 64, 500), ("randinit", False, 9, 461)):
+    for tag, fast, B, T, gru in (("vn", True, 64, 500, 1), ("randinit", False, 9, 461, 0), ("randinit", True, 9, 461, 2),
+                                 ("vn", True, 64, 500, 0)):
         m, w = _model(tag, fast)
         gen = torch.Generator().manual_seed(B)
         f0 = (100.0 + 500.0 * torch.rand(B, 1, T, generator=gen)).cuda()
@@ -557,16 +596,55 @@ def test_pipelined_forward_equals_serial():
         u, noise = oracle.draw_rng(T, 3)
         args = dict(phase_shift=u.reshape(-1).cuda(), noise=noise.cuda())
         eng = m._engine_for(f0)
+        eng.set_gru_impl(gru)   # 1: tensor-core recurrence at 64 utterances (one launch, progress marks), 2: forced, 0: fp32 blocks
         with torch.no_grad():
             eng.set_pipeline(False)
             serial = m(f0, control, **args).clone()
             eng.set_pipeline(True)
             piped = m(f0, control, **args)
             piped2 = m(f0, control, **args)
+            if gru:   # captured: per-block launches + events instead of the waiting kernels
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    yg = m(f0, control, **args)
+                g.replay()
         torch.cuda.synchronize()
+        eng.set_gru_impl(1)
         assert torch.isfinite(serial).all()
         assert torch.equal(piped, piped2)
         assert err(serial, piped)[0] < 1e-6 * max(1.0, float(serial.abs().max())), (tag, err(serial, piped))
+        if gru:
+            assert err(serial, yg)[0] < 1e-6 * max(1.0, float(serial.abs().max())), (tag, err(serial, yg))
+
+
+@pytest.mark.parametrize("B,T,fast,pipe", [(1, 500, True, False), (3, 131, False, False), (9, 461, True, True), (64, 500, True, True)])
+def test_noise_branch_inside_audio_kernel(B, T, fast, pipe):
+    """The FIR noise branch inside the fused audio kernel (nws_set_noise_fused(1): filtered by the MMA warps in the
+    shadow of the epilogue) against the separate nws_noise_filter_kernel launch (default): the same arithmetic with frames paired differently in the two-for-one FFTs — equal to fp32
+    round-off — for whole utterances, ragged chunks of hops, block-by-block rendering; and against the oracle."""
+    m, w = _model("randinit", fast)
+    gen = torch.Generator().manual_seed(7 * B + T)
+    f0, control = torch.rand(B, 1, T, generator=gen), torch.rand(B, 2, T, generator=gen)
+    u, noise = oracle.draw_rng(T, 11)
+    args = dict(phase_shift=u.reshape(-1).cuda(), noise=noise.cuda())
+    eng = m._engine_for(f0.cuda())
+    try:
+        eng.set_pipeline(pipe)
+        with torch.no_grad():
+            eng.set_noise_fused(False)
+            sep = m(f0.cuda(), control.cuda(), **args).clone()
+            eng.set_noise_fused(True)
+            fused = m(f0.cuda(), control.cuda(), **args).clone()
+            fused2 = m(f0.cuda(), control.cuda(), **args)
+    finally:
+        eng.set_noise_fused(False)
+        eng.set_pipeline(True)
+    assert torch.equal(fused, fused2)
+    assert err(fused, sep)[0] < 1e-6 * max(1.0, float(sep.abs().max())), err(fused, sep)
+    if B <= 3:
+        lut = oracle.build_lookup_table(w) if fast else None
+        ref = oracle.forward(w, f0, control, u, noise, lut=lut)
+        assert err(fused, ref)[0] < TOL_RAND, err(fused, ref)
 
 
 def test_host_pipeline_matches_direct_forwards():
