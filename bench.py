@@ -531,14 +531,49 @@ def config_c5(args, model, dev, rank, world, dist):
     tot_max, _ = aggregate_throughput(f_ms + g_ms, 0.0, dev)
     f_max, _ = aggregate_throughput(f_ms, 0.0, dev)
     g_max, _ = aggregate_throughput(g_ms, 0.0, dev)
-    return {"workload": "%s forward of a global batch of %d utterances x %g s sharded over %d GPU(s) + NCCL gather of the audio "
-                        "(BASELINE.json configs[4])" % ("FastNEWT" if args.variant == "fastnewt" else "NEWT", G, args.seconds, world),
-            "global_batch": G, "utterances_per_gpu": hi - lo, "n_gpus": world, "scaling": "strong", "steps": k,
-            "forward_ms_max": f_max, "gather_ms_max": g_max, "ms_per_job_max": tot_max,
-            "gather": ("ncclAllGather of [%d, %d] fp32 per rank (%.1f MB in, %.1f MB out per rank)" %
-                       (hi - lo, N, (hi - lo) * N * 4 / 1e6, G * N * 4 / 1e6)) if world > 1 else "single rank: nothing to gather",
-            "value": G * N / (tot_max * 1e-3), "value_forward_only": G * N / (f_max * 1e-3), "unit": "samples/s",
-            "gathered_shape_ok": shape_ok, "parity": par}
+    res = {"workload": "%s forward of a global batch of %d utterances x %g s sharded over %d GPU(s) + NCCL gather of the audio "
+                       "(BASELINE.json configs[4])" % ("FastNEWT" if args.variant == "fastnewt" else "NEWT", G, args.seconds, world),
+           "global_batch": G, "utterances_per_gpu": hi - lo, "n_gpus": world, "scaling": "strong", "steps": k,
+           "forward_ms_max": f_max, "gather_ms_max": g_max, "ms_per_job_max": tot_max,
+           "gather": ("ncclAllGather of [%d, %d] fp32 per rank straight into the full batch (%.1f MB in, %.1f MB out per rank)" %
+                      (hi - lo, N, (hi - lo) * N * 4 / 1e6, G * N * 4 / 1e6)) if world > 1 else "single rank: nothing to gather",
+           "value": G * N / (tot_max * 1e-3), "value_forward_only": G * N / (f_max * 1e-3), "unit": "samples/s",
+           "gathered_shape_ok": shape_ok, "parity": par}
+    # the same job in two waves per rank, the gather of wave 0 overlapping the forward of wave 1
+    # (sharding.forward_and_gather: wave w = rows [w G/2, (w+1) G/2) split over the ranks)
+    waves = 2
+    if world > 1 and G % (world * waves) == 0:
+        from neural_waveshaping_synthesis_b200.sharding import forward_and_gather, wave_bounds
+        rows = torch.cat([torch.arange(*wave_bounds(G, rank, world, waves, w)) for w in range(waves)])
+        f0_w, control_w = f0_all[rows].contiguous().to(dev), control_all[rows].contiguous().to(dev)
+        ov = []
+        with torch.no_grad():
+            for i in range(2 + k):
+                torch.cuda.synchronize(dev)
+                dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                full = forward_and_gather(model, f0_w, control_w, G, waves=waves, phase_shift=u, noise=noise)
+                b.record()
+                torch.cuda.synchronize(dev)
+                if i >= 2:
+                    ov.append(a.elapsed_time(b))
+            par_w = {}
+            for j in sorted({0, G // 2, G - 1}):
+                solo = model(f0_all[j:j + 1].to(dev), control_all[j:j + 1].to(dev), phase_shift=u, noise=noise)
+                par_w["row%d_vs_solo_max_abs" % j] = float((full[j] - solo[0]).abs().max())
+            ok_w = tuple(full.shape) == (G, N)
+            del full
+        ov_max, _ = aggregate_throughput(sum(ov) / k, 0.0, dev)
+        res["overlapped"] = {"protocol": "%d waves per rank; ncclAllGather of wave w (async, into its rows of the full batch) "
+                                         "beside the forward of wave w+1" % waves,
+                             "ms_per_job_max": ov_max, "value": G * N / (ov_max * 1e-3), "unit": "samples/s",
+                             "gathered_shape_ok": ok_w, "parity": par_w}
+        if ov_max < tot_max:
+            res["value_serial_protocol"] = res["value"]
+            res["value"] = res["overlapped"]["value"]
+            res["ms_per_job_max_serial_protocol"], res["ms_per_job_max"] = tot_max, ov_max
+    return res
 
 
 def workload_config(args):
@@ -661,6 +696,19 @@ def run_b200(args):
                 stage_acc[k] = stage_acc.get(k, 0.0) + v / args.steps
         eng.set_profiling(False)
 
+        # ---- the library's alternatives on the same workload (A/B, same timing as `value`): the fp32 SIMT recurrence
+        # instead of the tensor-core one, and the FIR noise branch inside the fused audio kernel instead of its own launch
+        variants_ms = {"default": step_ms}
+        k_ab = max(5, min(args.steps, 30))
+        for name, on, off in (("gru_fp32_simt", lambda: eng.set_gru_impl(0), lambda: eng.set_gru_impl(1)),
+                              ("noise_branch_in_audio_kernel", lambda: eng.set_noise_fused(True), lambda: eng.set_noise_fused(False))):
+            on()
+            for _ in range(3):
+                model(f0, control)
+            per = timed_steps(k_ab, lambda: model(f0, control))
+            off()
+            variants_ms[name] = sum(per) / len(per)
+
         # ---- end to end through the public API for host-resident batches (streaming.HostPipeline, the loop of
         # scripts/resynthesise_dataset.py): every step copies its inputs from pinned host memory, runs the forward
         # and reads the audio back to pinned host memory; upload of step i+1 and download of step i-1 overlap the
@@ -763,6 +811,9 @@ def run_b200(args):
                      "issue_view": issue_view(args.variant, audio_ms, clocks, ffma_tflops)},
         "stages_ms": stage_acc,
         "stages_order": "serial (stage profiling disables the pipelined order; `ms_per_step` is the pipelined forward)",
+        "recurrence": ("tensor cores (mma.sync m16n8k16, fp16-split operands, 8 utterances per CTA: csrc/nws_gru_mma.cu)"
+                       if B >= 64 else "fp32 SIMT, one utterance per CTA (fewer than 64 utterances)"),
+        "variants_ms_per_step_rank0": variants_ms,
         "host_affinity": affinity,
     }
     if configs:
