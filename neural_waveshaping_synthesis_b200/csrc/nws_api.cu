@@ -577,10 +577,16 @@ extern "C" int nws_forward(NwsHandle ctx, const float* f0, const float* control,
       NWS_CUDA_OK(cudaEventRecord(ctx->ev_mlp[k], c));
       // hop h blends towards frame h + 1: the block's last frame waits for the next block
       const int hb = k == 0 ? 0 : tb[k] - 1, he = last ? T : tb[k + 1] - 1;
-      // the noise branch: inside the audio kernel (default), or its own launch writing into `dry` first
+      // Grid of the block's audio launch.  Per-block encoder launches: capped to the SMs the encoder does not use, so
+      // that its next launch finds them free.  One encoder launch (progress marks): no cap — CTAs that find no free SM
+      // wait in the hardware queue and start when the encoder's CTAs leave, claiming whatever tiles remain (a cap
+      // decided at launch time strangled large batches: with 128 encoder CTAs every block rendered on 20 SMs long after
+      // the encoder had finished).
+      const int audio_cap = (last || gru_marks) ? 0 : ctx->sm_count - gru_ctas;
+      // the noise branch: its own launch writing into `dry` first (default), or inside the audio kernel
       if (!ctx->noise_fused) NWS_TRY(nws_launch_noise_filter(ctx, w.bands, w.xspec, w.dry, B, T, hb, he, c));
       NWS_TRY(nws_launch_audio_tc(ctx, f0, w.carry, w.film, u_phase, ctx->noise_fused ? nullptr : w.dry, w.dry, nullptr, B, T, hb, he,
-                                  ctx->tile_counters + (on_aux ? 2 : 0), use_lut, c, last ? 0 : ctx->sm_count - gru_ctas, false,
+                                  ctx->tile_counters + (on_aux ? 2 : 0), use_lut, c, audio_cap, false,
                                   ctx->noise_fused ? w.bands : nullptr, w.xspec));
       g_tl.mark(on_aux ? "block chain (aux)" : "block chain", c);
       if (on_aux) { NWS_CUDA_OK(cudaEventRecord(ctx->ev_early_done, aux)); aux_used = true; }

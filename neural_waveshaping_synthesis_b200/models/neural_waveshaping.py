@@ -170,8 +170,10 @@ class NeuralWaveshaping(nn.Module):
         object.__setattr__(self, "_wt_cache", None)
         return super().load_state_dict(*args, **kwargs)
 
-    def _engine_for(self, like: torch.Tensor) -> NwsEngine:
-        """The engine of the input's device with this module's current weights (and lookup table) loaded.
+    def _engine_for(self, like: torch.Tensor, lane: int = 0) -> NwsEngine:
+        """The engine of the input's device with this module's current weights (and lookup table) loaded.  `lane` > 0
+        selects a further, independent engine of the same device (own C context: streams, workspace, scheduler
+        counters) so that two forwards can be in flight on two streams at once (streaming.HostPipeline).
 
         Called on every forward, so the up-to-date check is kept cheap (a 256-sample forward is ~35 us of GPU work):
         sub-module identity (`model.newt = FastNEWT(model.newt)`), moves and casts (`_apply`), `load_state_dict`, and
@@ -181,10 +183,11 @@ class NeuralWaveshaping(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("NeuralWaveshaping (B200) runs on CUDA only: inputs are on %s. There is no CPU "
                                "fallback; move the model and inputs with .to('cuda')." % dev)
-        eng = self._engines.get(dev)
+        slot = dev if lane == 0 else (dev, lane)
+        eng = self._engines.get(slot)
         if eng is None:
             eng = NwsEngine(dev)
-            self._engines[dev] = eng
+            self._engines[slot] = eng
             for m in self.modules():
                 if isinstance(m, BoundToRoot):
                     m._bind_root(self)
@@ -194,7 +197,7 @@ class NeuralWaveshaping(nn.Module):
         except Exception:     # tensors created under torch.inference_mode() do not track versions
             vsum = -1
         fast = self.newt.lookup_table if isinstance(self.newt, FastNEWT) else None
-        tag = self._loaded.get(dev)
+        tag = self._loaded.get(slot)
         key = (self._wt_cache[3], vsum)      # (generation of the tensor list, sum of the in-place version counters)
         if tag is None or tag[0] != key:
             if tensors[0].device != dev:
@@ -209,7 +212,7 @@ class NeuralWaveshaping(nn.Module):
             if tag[1] != lsig:
                 eng.set_lut(fast, self.newt.table_min, self.newt.table_max)
                 tag = (tag[0], lsig)
-        self._loaded[dev] = tag
+        self._loaded[slot] = tag
         return eng
 
     # ------------------------------------------------------------------ reference API
@@ -229,8 +232,12 @@ class NeuralWaveshaping(nn.Module):
         torch.initial_seed()."""
         if not isinstance(f0, torch.Tensor) or not isinstance(control, torch.Tensor):
             raise TypeError("f0 and control must be tensors")
-        eng = self._engine_for(f0)
-        return eng.forward(f0, control, u_phase=phase_shift, noise=noise, use_lut=isinstance(self.newt, FastNEWT))
+        return self._forward_lane(0, f0, control, phase_shift, noise)
+
+    def _forward_lane(self, lane, f0, control, phase_shift=None, noise=None, out=None):
+        """forward() through engine `lane` of the input's device (lane 0 = the one every other entry point uses)."""
+        eng = self._engine_for(f0, lane)
+        return eng.forward(f0, control, u_phase=phase_shift, noise=noise, use_lut=isinstance(self.newt, FastNEWT), out=out)
 
     def synthesise_from_host(self, f0, control, out=None, phase_shift=None, noise=None):
         """Host tensors in, host tensor out through nws_forward_host (H2D, forward, D2H, sync)."""

@@ -18,15 +18,24 @@ HOP = 128
 class HostPipeline:
     """`for meta, audio in HostPipeline(model, device).run(batches)`; `batches` yields `(f0, control)` or
     `(f0, control, meta)` with host tensors (pinned memory if the copies are to be asynchronous).  `audio` is
-    a pinned host tensor [B, 128*T], valid until the next iteration of the generator."""
+    a pinned host tensor [B, 128*T], valid until the next iteration of the generator.
 
-    def __init__(self, model, device):
+    Batch i is uploaded on one stream, rendered on compute stream i % lanes by engine i % lanes, and downloaded on a third
+    stream.  With `lanes` = 2 (default) two forwards are in flight: a forward starts with its encoder alone on a few SMs
+    and ends with a reverb tail, and at 64 utterances those edges are a quarter of its latency (0.98 ms against 0.73 ms
+    of work at the chip's large-batch rate) — the neighbour batch fills them.  Results are yielded in order."""
+
+    def __init__(self, model, device, lanes: int = 2):
         self.model = model
         self.device = torch.device(device)
+        self.lanes = max(1, int(lanes))
+        self.depth = 2 * self.lanes          # staging slots (device inputs / device outputs / pinned results)
         self.up_stream = torch.cuda.Stream(self.device)
         self.down_stream = torch.cuda.Stream(self.device)
-        self._dev_in = [None, None]
-        self._host_out = [None, None]
+        self.compute = [torch.cuda.Stream(self.device) for _ in range(self.lanes)] if self.lanes > 1 else None
+        self._dev_in = [None] * self.depth
+        self._dev_out = [None] * self.depth
+        self._host_out = [None] * self.depth
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -50,46 +59,63 @@ class HostPipeline:
 
     def run(self, batches):
         it = iter(batches)
-        main = torch.cuda.current_stream(self.device)
+        caller = torch.cuda.current_stream(self.device)
+        D = self.depth
         try:
             staged = self._upload(next(it), 0, None)
         except StopIteration:
             return
-        done_prev = None          # end of forward i-1 (the last reader of slot (i+1)&1)
-        pending = None            # (event, meta, host tensor) of step i-1
+        done = [None] * D         # end of the forward that used staging slot s
+        landed = [None] * D       # end of the download out of staging slot s
+        pending = []              # (landed event, meta, host tensor) in batch order
         i = 0
         with torch.no_grad():
             while staged is not None:
                 (f0, control), ready, meta = staged
-                main.wait_event(ready)
-                y = self.model(f0, control)
-                done = torch.cuda.Event()
-                done.record(main)
+                slot, lane = i % D, i % self.lanes
+                cs = self.compute[lane] if self.compute else caller
+                T = f0.shape[-1]
+                y = self._dev_out[slot]
+                if y is None or y.shape != (f0.shape[0], T * HOP):
+                    y = torch.empty(f0.shape[0], T * HOP, dtype=torch.float32, device=self.device)
+                    self._dev_out[slot] = y
+                with torch.cuda.stream(cs):
+                    cs.wait_event(ready)
+                    if landed[slot] is not None:
+                        cs.wait_event(landed[slot])    # the download that last read this output buffer
+                    self.model._forward_lane(lane, f0, control, out=y)
+                    d = torch.cuda.Event()
+                    d.record(cs)
+                done[slot] = d
                 try:                                   # stage the next batch before this result's download
-                    staged = self._upload(next(it), (i + 1) & 1, done_prev)
+                    nxt = (i + 1) % D
+                    staged = self._upload(next(it), nxt, done[nxt])
                 except StopIteration:
                     staged = None
-                slot = i & 1
                 host = self._host_out[slot]
                 if host is None or host.shape != y.shape:
                     host = torch.empty(y.shape, dtype=torch.float32).pin_memory()
                     self._host_out[slot] = host
                 with torch.cuda.stream(self.down_stream):
-                    self.down_stream.wait_event(done)
+                    self.down_stream.wait_event(d)
                     host.copy_(y, non_blocking=True)
-                    y.record_stream(self.down_stream)
-                    landed = torch.cuda.Event()
-                    landed.record(self.down_stream)
+                    ev = torch.cuda.Event()
+                    ev.record(self.down_stream)
+                landed[slot] = ev
                 self.d2h_bytes += y.numel() * 4
-                if pending is not None:
-                    pending[0].synchronize()
-                    yield pending[1], pending[2]
-                pending = (landed, meta, host)
-                done_prev = done
+                pending.append((ev, meta, host))
+                # keep `lanes` batches in flight; a yielded host tensor is not rewritten before D - lanes further batches
+                if len(pending) > self.lanes:
+                    ev0, m0, h0 = pending.pop(0)
+                    ev0.synchronize()
+                    yield m0, h0
                 i += 1
-        if pending is not None:
-            pending[0].synchronize()
-            yield pending[1], pending[2]
+        for ev0, m0, h0 in pending:
+            ev0.synchronize()
+            yield m0, h0
+        if self.compute:
+            for cs in self.compute:                    # leave the caller's stream ordered after everything issued here
+                caller.wait_stream(cs)
 
 
 class SynthStream:

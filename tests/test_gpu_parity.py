@@ -650,21 +650,22 @@ def test_noise_branch_inside_audio_kernel(B, T, fast, pipe):
         assert err(fused, ref)[0] < TOL_RAND, err(fused, ref)
 
 
-def test_host_pipeline_matches_direct_forwards():
-    """streaming.HostPipeline (upload i+1 / forward i / download i-1 on three streams) returns, batch by batch,
-    exactly what direct forwards on the same inputs and the same RNG stream return — including a ragged last
-    batch and metadata passed through."""
+@pytest.mark.parametrize("lanes", [2, 1])
+def test_host_pipeline_matches_direct_forwards(lanes):
+    """streaming.HostPipeline (uploads, forwards on `lanes` compute streams / engines, downloads: all overlapped) returns,
+    batch by batch and in order, exactly what direct forwards on the same inputs and the same RNG stream return —
+    including full-size batches (pipelined order, two in flight), a ragged last batch and metadata passed through."""
     from neural_waveshaping_synthesis_b200.streaming import HostPipeline
     m, _ = _model("vn", True)
     gen = torch.Generator().manual_seed(5)
-    shapes = [(16, 64), (16, 64), (16, 64), (16, 64), (5, 37)]
+    shapes = [(16, 64), (64, 500), (64, 500), (16, 64), (64, 500), (16, 64), (16, 64), (5, 37)]
     batches = [((100.0 + 400.0 * torch.rand(B, 1, T, generator=gen)).pin_memory(),
                 torch.randn(B, 2, T, generator=gen).pin_memory(), "batch%d" % i) for i, (B, T) in enumerate(shapes)]
     torch.manual_seed(11)
     with torch.no_grad():
         direct = [m(f0.cuda(), c.cuda()).cpu() for f0, c, _ in batches]
     torch.manual_seed(11)
-    pipe = HostPipeline(m, "cuda:0")
+    pipe = HostPipeline(m, "cuda:0", lanes=lanes)
     got = [(meta, audio.clone()) for meta, audio in pipe.run(iter(batches))]
     assert [g[0] for g in got] == [b[2] for b in batches]
     for (meta, audio), ref in zip(got, direct):
