@@ -7,18 +7,23 @@
 //                pre-split into tf32 hi / lo and pre-arranged in the canonical UMMA K-major layout
 //   D          = accumulator in TMEM (two 128-column regions, alternating per weight block)
 //   D += A_hi B_hi + A_lo B_hi + A_hi B_lo  (3xTF32: fp32-level accuracy)
-//   epilogue   = each thread owns one frame row: TMEM -> registers, bias, LayerNorm over the row's 128
-//                channels entirely in-thread, LeakyReLU, hi/lo split, tcgen05.st back as the next A
+//   epilogue   = two threads per frame row, 64 channels each (the two epilogue warpgroups read the same TMEM lanes):
+//                TMEM -> registers, bias, LayerNorm over the row's 128 channels (in-thread partial sums, the two halves
+//                exchanged through shared memory), LeakyReLU, hi/lo split, tcgen05.st back as the next A.  One thread per
+//                row was a lone warp per scheduler running 1,700 dependent instructions per block at IPC 0.2 — the
+//                epilogue, not the MMAs (34 % of the time), set the kernel's pace.
 //
-// Warp roles (192 threads): warps 0-3 epilogue warpgroup (thread = frame), warp 4 weight producer,
-// warp 5 MMA issuer.  Block sequence per tile: proj, A1, A2, A3, Aout[0:128], Aout[128:256],
+// Warp roles (320 threads): warps 0-7 two epilogue warpgroups (thread = frame x channel half), warp 8 weight
+// producer, warp 9 MMA issuer.  Block sequence per tile: proj, A1, A2, A3, Aout[0:128], Aout[128:256],
 // proj (again, from a reload of the GRU states), B1, B2, B3, Bout[0:128], Bout[128:144].
 #include "nws_internal.cuh"
 #include "nws_tc.cuh"
 
 namespace {
 
-constexpr int kMlpThreads = 192;
+constexpr int kMlpThreads = 320;
+constexpr int kEpiThreads = 256;           // two epilogue warpgroups
+constexpr int kHalf = kEmb / 2;              // channels per epilogue thread
 constexpr int kSlots = 4;
 constexpr int kChunkK = 32;                 // K elements per ring chunk (4 MMA k-steps)
 constexpr int kSlotBytes = 2 * 128 * kChunkK * 4;  // hi + lo of a [128 x 32] chunk = 32 KB
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
   __shared__ uint32_t tmem_base_s;
   __shared__ int fault_s;
   __shared__ __align__(16) float vec_s[kBlocks * kVecStride];
+  __shared__ float ln_sum[2][128], ln_sq[2][128];   // LayerNorm partial sums of the two channel halves of a row
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int seg = p.t_end - p.t_begin, tiles_per_seg = (seg + 127) / 128;
   const int n_tiles = (p.M / p.T) * tiles_per_seg;
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
 
   if (tid == 0) {
     for (int s = 0; s < kSlots; ++s) { nws_mbar_init(&full_bar[s], 1); nws_mbar_init(&empty_bar[s], 1); }
-    nws_mbar_init(&a_ready, 128);
+    nws_mbar_init(&a_ready, kEpiThreads);
     nws_mbar_init(&d_ready[0], 1);
     nws_mbar_init(&d_ready[1], 1);
     nws_fence_mbar_init();
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
   nws_tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ================= weight producer: one lane streams every block's chunks through the ring
     if (lane == 0) {
       uint32_t n_fill = 0;   // chunks issued so far (slot = n_fill % kSlots)
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
       }
       if (!ok) fault_s = 1;
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ================= MMA issuer: the whole warp walks the block sequence (waits included) with warp-uniform
     // operands — tensor-memory base broadcast from lane 0, descriptors from kernel parameters and constants — and
     // one elected lane issues, so the MMAs go out back to back from uniform registers (a lone lane-0 thread made
@@ -200,21 +206,23 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
       if (!ok && lane == 0) fault_s = 1;
     }
   } else {
-    // ================= epilogue warpgroup: thread = frame row = TMEM lane
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    // ================= epilogue warpgroups: thread = (frame row = TMEM lane, channel half)
+    const int half = tid >> 7, r = tid & 127, ch0 = half * kHalf;
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    auto epi_barrier = [] { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
     uint32_t n_blk = 0;
     bool ok = true;
     for (int tile = item0; tile < n_tiles && ok; tile += item_step) {
       const int ub = tile / tiles_per_seg, tk = tile - ub * tiles_per_seg;
-      const int row = ub * p.T + p.t_begin + tk * 128 + tid;
-      const bool valid = tk * 128 + tid < seg;
+      const int row = ub * p.T + p.t_begin + tk * 128 + r;
+      const bool valid = tk * 128 + r < seg;
       const float* hrow = p.h + (size_t)(valid ? row : 0) * kEmb;
       for (int b = b_begin; b < b_end && ok; ++b, ++n_blk) {
         const MlpBlockDesc d = p.blk[b];
         if (b == 0 || b == 6) {
           // A <- this frame's GRU state (the embedding projection's input), hi/lo split
 #pragma unroll 1
-          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+          for (int c0 = ch0; c0 < ch0 + kHalf; c0 += 16) {
             float y[16];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -234,61 +242,65 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
         const uint32_t drow = tmem_row + kColD + (n_blk & 1) * 128;
         const float* bias = vec_s + b * kVecStride;
         if (d.kind == 1) {
-          // the whole 128-channel row in registers: one burst of TMEM loads, then LayerNorm (dynamic.py:11-17)
-          // entirely in-thread with four independent accumulation chains
+          // this thread's 64 channels of the row in registers: one burst of TMEM loads, then LayerNorm (dynamic.py:11-17)
+          // with four independent accumulation chains; the row's other half adds its sums through shared memory
           const float* g = bias + 128;
           const float* be = bias + 256;
-          float x[kEmb];
+          float x[kHalf];
 #pragma unroll
-          for (int c0 = 0; c0 < kEmb; c0 += 16) nws_tmem_ld16_nowait(drow + c0, x + c0);
+          for (int c0 = 0; c0 < kHalf; c0 += 16) nws_tmem_ld16_nowait(drow + ch0 + c0, x + c0);
           nws_tmem_wait_ld();
 #pragma unroll
-          for (int c0 = 0; c0 < kEmb; c0 += 16) nws_reg_fence16(x + c0);
+          for (int c0 = 0; c0 < kHalf; c0 += 16) nws_reg_fence16(x + c0);
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-          for (int c = 0; c < kEmb; c += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(bias + c);
+          for (int c = 0; c < kHalf; c += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias + ch0 + c);
             x[c] += bv.x; x[c + 1] += bv.y; x[c + 2] += bv.z; x[c + 3] += bv.w;
             s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3];
           }
-          const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / kEmb);
+          ln_sum[half][r] = (s0 + s1) + (s2 + s3);
+          epi_barrier();
+          const float mean = (ln_sum[0][r] + ln_sum[1][r]) * (1.0f / kEmb);
           float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-          for (int c = 0; c < kEmb; c += 4) {
+          for (int c = 0; c < kHalf; c += 4) {
             x[c] -= mean; x[c + 1] -= mean; x[c + 2] -= mean; x[c + 3] -= mean;
             q0 = fmaf(x[c], x[c], q0); q1 = fmaf(x[c + 1], x[c + 1], q1);
             q2 = fmaf(x[c + 2], x[c + 2], q2); q3 = fmaf(x[c + 3], x[c + 3], q3);
           }
-          const float rstd = 1.0f / sqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / kEmb) + 1e-5f);
+          ln_sq[half][r] = (q0 + q1) + (q2 + q3);
+          epi_barrier();
+          const float rstd = 1.0f / sqrtf((ln_sq[0][r] + ln_sq[1][r]) * (1.0f / kEmb) + 1e-5f);
 #pragma unroll
-          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+          for (int c0 = 0; c0 < kHalf; c0 += 16) {
             float y[16];
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
-              const float4 gv = *reinterpret_cast<const float4*>(g + c0 + i);
-              const float4 bv = *reinterpret_cast<const float4*>(be + c0 + i);
+              const float4 gv = *reinterpret_cast<const float4*>(g + ch0 + c0 + i);
+              const float4 bv = *reinterpret_cast<const float4*>(be + ch0 + c0 + i);
               const float t0 = fmaf(x[c0 + i] * rstd, gv.x, bv.x), t1 = fmaf(x[c0 + i + 1] * rstd, gv.y, bv.y);
               const float t2 = fmaf(x[c0 + i + 2] * rstd, gv.z, bv.z), t3 = fmaf(x[c0 + i + 3] * rstd, gv.w, bv.w);
               y[i] = t0 > 0.f ? t0 : 0.01f * t0; y[i + 1] = t1 > 0.f ? t1 : 0.01f * t1;
               y[i + 2] = t2 > 0.f ? t2 : 0.01f * t2; y[i + 3] = t3 > 0.f ? t3 : 0.01f * t3;
             }
-            store_a16(tmem_row, c0, y);
+            store_a16(tmem_row, ch0 + c0, y);
           }
           tmem_wait_st();
           nws_tc_fence_before();
           mbar_arrive(&a_ready);
         } else if (d.kind == 0) {
-          float x[kEmb];
+          float x[kHalf];
 #pragma unroll
-          for (int c0 = 0; c0 < kEmb; c0 += 16) nws_tmem_ld16_nowait(drow + c0, x + c0);
+          for (int c0 = 0; c0 < kHalf; c0 += 16) nws_tmem_ld16_nowait(drow + ch0 + c0, x + c0);
           nws_tmem_wait_ld();
 #pragma unroll
-          for (int c0 = 0; c0 < kEmb; c0 += 16) nws_reg_fence16(x + c0);
+          for (int c0 = 0; c0 < kHalf; c0 += 16) nws_reg_fence16(x + c0);
 #pragma unroll
-          for (int c0 = 0; c0 < kEmb; c0 += 16) {
+          for (int c0 = 0; c0 < kHalf; c0 += 16) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[c0 + i] += bias[c0 + i];
-            store_a16(tmem_row, c0, x + c0);
+            for (int i = 0; i < 16; ++i) x[c0 + i] += bias[ch0 + c0 + i];
+            store_a16(tmem_row, ch0 + c0, x + c0);
           }
           tmem_wait_st();
           nws_tc_fence_before();
@@ -298,8 +310,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) nws_mlp_tc_kernel(const MlpTcP
           float* orow = film ? p.film + (size_t)(valid ? row : 0) * kFilm + d.col0
                              : p.bands + (size_t)(valid ? row : 0) * kBandsPad + d.col0;
           const int n_store = film ? 128 : (d.n == 128 ? 128 : kBandsPad - 128);
+          // a 128-column block: each half its 64 columns; the 16-column tail of the band gains: the first half only
+          const int c_lo = d.n == 128 ? ch0 : 0, c_hi = d.n == 128 ? ch0 + kHalf : (half == 0 ? d.n : 0);
 #pragma unroll 1
-          for (int c0 = 0; c0 < d.n; c0 += 16) {
+          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
             float v[16];
             nws_tmem_ld16(drow + c0, v);
             if (valid) {
