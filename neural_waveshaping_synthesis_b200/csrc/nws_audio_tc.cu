@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
   const uint32_t w_hi_addr = nws_smem_u32(smem + C::oW), w_lo_addr = w_hi_addr + kWBytes;
   const float mix_b = p.mix_b[0];
   const float inv_hop = (float)T / (float)N;
+  const float lut_scale = USE_LUT ? (float)p.lut_size / p.lut_span : 1.0f;   // table positions per unit of shaper input
   const int hops = p.t_end - p.t_begin;
   const int n_tiles = p.B * hops;   // < 2^31 (checked by the launcher)
   const uint32_t hops_magic = p.hops_magic;
@@ -577,6 +578,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
       float4 lo4, hi4;
       lo4.x = fa[0]; lo4.y = fb[0] - fa[0];
       lo4.z = fmaf(lo4.x, bw.x, fa[kShapers]); lo4.w = fmaf(lo4.y, bw.x, fb[kShapers] - fa[kShapers]);
+      if (USE_LUT) {
+        // FastNEWT: the table position idx = size * (x - min) / span (shaping.py:137) is affine in x, so it is folded
+        // into the FiLM-in coefficients here, once per (half hop, channel): the per-sample loop gets idx straight out
+        // of its three FMAs instead of x and a four-instruction bit-exact division after it.  idx then differs from
+        // the reference's operation order by about an ulp — the size of what the rounding of x itself moves it by —
+        // and where that flips floor(idx) the interpolant is continuous.  (The stage entry nws_stage_lut_lookup keeps
+        // the reference's exact sequence: identical inputs -> identical indices and values.)
+        lo4.x *= lut_scale; lo4.y *= lut_scale; lo4.z = (lo4.z - p.lut_min) * lut_scale; lo4.w *= lut_scale;
+      }
       hi4.x = bw.y * fa[2 * kShapers]; hi4.y = bw.y * (fb[2 * kShapers] - fa[2 * kShapers]);
       hi4.z = (!USE_LUT && SHP == 1) ? sm_scale[c] : 0.f; hi4.w = 0.f;   // SHP 1: the shaper's input scale rides along
       float ka = bw.y * fa[3 * kShapers], kd = bw.y * (fb[3 * kShapers] - fa[3 * kShapers]);
@@ -707,8 +717,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
     // FastNEWT: MODE 2 = the table size is the reference's default 4096 (shaping.py:101), known at compile time
     // so a row offset is an immediate; MODE 1 = any size.  Offsets are 32-bit (a table is < 4 GB).
     const int lut_size = (USE_LUT && MODE == 2) ? 4096 : p.lut_size;
-    const float lut_size_f = (float)lut_size;
-    const float lut_min = p.lut_min, lut_span = p.lut_span, lut_rcp = p.lut_span_rcp;
     float mix_a = 0.f, mix_d = 0.f;
     if constexpr (!USE_LUT && SHP == 1) {
       // NEWT (shaping.py:15-37) with the two 8x8 layers of every shaper on the tensor cores (mma.sync m16n8k8, 3xTF32):
@@ -810,14 +818,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) nws_audio_tc_kernel(const NwsAu
         if (TAP) p.exciter_out[((size_t)b * kShapers + c) * N + n] = ev[i] + sm_bw[c].x;
         const float4 ci = cf[2 * c];
         const float2 cn = *reinterpret_cast<const float2*>(&cf[2 * c + 1]);
-        const float x = fmaf(l1, fmaf(ci.y, ev[i], ci.w), fmaf(ci.x, ev[i], ci.z));
-        // FastNEWT.shaping_fn (shaping.py:136-151): same index arithmetic as nws_lut_index — floor and clamp
-        // done on the integer side (F2I.FLOOR saturates, NaN -> 0 with a NaN fract, as floorf/fmaxf/fminf give);
-        // the table row holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
-        // MODE 2 (size 4096 = 2^12): the multiply by the size is folded into the division's constants — scaling
-        // by a power of two commutes with every rounding of the Markstein sequence, so idx is bit-identical
-        const float idx = MODE == 2 ? nws_lut_idx_pow2(x, lut_min, lut_span * (1.0f / 4096.0f), lut_rcp * 4096.0f)
-                                    : nws_div_markstein(NWS_MUL(lut_size_f, NWS_ADD(x, -lut_min)), lut_span, lut_rcp);
+        // FastNEWT.shaping_fn (shaping.py:136-151): FiLM-in and the table position in one affine map (coefficient
+        // table above); floor and clamp done on the integer side (F2I.FLOOR saturates, NaN -> 0 with a NaN fract, as
+        // floorf/fmaxf/fminf give); the table row holds (L, U - L) pairs so one 8-byte load feeds (U - L) * fract + L
+        const float idx = fmaf(l1, fmaf(ci.y, ev[i], ci.w), fmaf(ci.x, ev[i], ci.z));
         const int fi = nws_min_relu(__float2int_rd(idx), lut_size - 1);   // clamp to [0, size-1]: one VIMNMX.RELU
         const float2 t2 = __ldg(lut_row + i * lut_size + (uint32_t)fi);
         const float y = fmaf(t2.y, NWS_ADD(idx, -(float)fi), t2.x);

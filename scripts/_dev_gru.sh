@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-# serial forward = launches: rng, phase_carry, noise_spectrum, gru, mlp_tc, noise_filter, audio, reverb x3 (+ first-call extras)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"nws_mlp_tc_kernel|nws_noise_filter_kernel|nws_reverb_" -s 10 -c 5 -f -o gpurun_out/r2_hop_kernels python scripts/dev_serial_forward.py fastnewt 4 > gpurun_out/ncu_hop.log 2>&1
-tail -3 gpurun_out/ncu_hop.log
+for cfg in "32 117" "32 156" "32 234" "64 218" "16 121" "125 125" "250 250" "32 94"; do set -- $cfg; NWS_PIPE_FIRST=$1 NWS_PIPE_BLOCK=$2 timeout 200 python scripts/dev_lanes.py fastnewt 64 2>&1 | grep -v Warn | tee -a gpurun_out/dev_lanes.log; done
+for ch in 4 16; do NWS_TILE_CHUNK=$ch timeout 200 python scripts/dev_lanes.py fastnewt 64 2>&1 | grep -v Warn | tee -a gpurun_out/dev_lanes.log; done
+for cfg in "32 117" "32 234" "125 125"; do set -- $cfg; NWS_PIPE_FIRST=$1 NWS_PIPE_BLOCK=$2 timeout 200 python scripts/dev_lanes.py newt 64 2>&1 | grep -v Warn | tee -a gpurun_out/dev_lanes.log; done
