@@ -368,11 +368,12 @@ def config_c3(args, cpu_model, dev, timed_steps, flush, peaks_hbm, clocks_now):
             model(f0, control)
         per = timed_steps(k, lambda: model(f0, control))
 
-        def make_inputs(i):
-            g = torch.Generator(device=dev).manual_seed(5000 + i)
-            return torch.rand(B, 1, T, device=dev, generator=g), torch.rand(B, 2, T, device=dev, generator=g)
+        g = torch.Generator(device=dev).manual_seed(5000)
         n_sets = (160 << 20) // ((f0.numel() + control.numel()) * 4) + 1
-        thr_ms = lane_throughput_ms(model, dev, make_inputs, k, n_sets)
+        f0_sets = torch.rand(n_sets, B, 1, T, device=dev, generator=g)
+        control_sets = torch.rand(n_sets, B, 2, T, device=dev, generator=g)
+        thr_ms = lane_throughput_ms(model, dev, lambda i: (f0_sets[i], control_sets[i]), k, n_sets)
+        del f0_sets, control_sets
         eng = model._engine_for(f0)
         eng.set_profiling(True)
         acc = {}
@@ -736,10 +737,13 @@ def run_b200(args):
         # ---- the timed region of `value`: K steps, two in flight
         n_sets = (160 << 20) // ((f0.numel() + control.numel()) * 4) + 1     # > the 126 MB L2
 
+        if args.inputs == "rand":   # two launches for all the sets (not two per set: they would crowd the launch list)
+            g = torch.Generator(device=dev).manual_seed(1000 * (1 + rank))
+            f0_sets = torch.rand(n_sets, B, 1, T, device=dev, generator=g)
+            control_sets = torch.rand(n_sets, B, 2, T, device=dev, generator=g)
+
         def make_inputs(i):
-            g = torch.Generator(device=dev).manual_seed(1000 * (1 + rank) + i)
-            return (torch.rand(B, 1, T, device=dev, generator=g), torch.rand(B, 2, T, device=dev, generator=g)) \
-                if args.inputs == "rand" else (f0, control)
+            return (f0_sets[i], control_sets[i]) if args.inputs == "rand" else (f0, control)
         barrier()
         lib.nws_launch_count(1)
         step_ms = lane_throughput_ms(model, dev, make_inputs, args.steps, n_sets if args.inputs == "rand" else 1)
