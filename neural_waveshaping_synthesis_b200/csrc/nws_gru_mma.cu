@@ -21,8 +21,13 @@
 // four registers of a k-tile ({b0, b1} x {h1, h2}) are one conflict-free LDS.128.
 //
 // Per step and CTA: 72 HMMA per warp (576 per SM) against 64 packed FMAs + 31 shuffles per thread for ONE
-// utterance in the fp32 kernel (nws_encoder.cu / nws_hop_bodies.cuh, kept for single utterances, the fused
-// short-buffer front end and as the cross-check: nws_set_gru_impl(0)).
+// utterance in the fp32 kernel (nws_encoder.cu / nws_hop_bodies.cuh).  Measured on B200 (profiles/r2_ncu_gru_mma.txt):
+// 1.18 us per step — the legacy HMMA pipe, one m16n8k16 per 8.5 cycles and scheduler, is 53 % of it, the gate
+// arithmetic (four cells per thread) the rest — against 0.70 us for the fp32 kernel, which needs one SM per utterance
+// where this one needs one per eight.  So the fp32 kernel stays for batches that do not fill the chip (fewer than 64
+// utterances: nws_gru_uses_mma), inside the fused short-buffer front end and the streaming path, and as the
+// cross-check (nws_set_gru_impl(0)); from 64 utterances on this kernel encodes, in ONE launch that publishes its
+// progress (marks) so that the rest of the forward can render the frames already encoded (nws_forward).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
