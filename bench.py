@@ -143,7 +143,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "source": self.source.replace("2 ms period", "2 ms period (5 ms during the e2e region)") if self.source else self.source}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def build_weights():
@@ -794,17 +794,10 @@ def run_b200(args):
         e2e_run(max(args.warmup, 3))
         barrier()
         pipe.h2d_bytes = pipe.d2h_bytes = 0
-        # the host thread is part of this measurement (it waits for results and issues the next batch): the NVML
-        # polling thread, whose calls contend with kernel launches inside the driver, backs off to 5 ms here (at 2 ms it
-        # cost the pipeline 7-10 %: 0.84-0.87 ms per batch against 0.78 ms without a sampler, scripts/dev_e2e_lanes.py)
-        if sampler:
-            sampler.period_s = float(os.environ.get("NWS_BENCH_E2E_SAMPLE_MS", "5")) * 1e-3
         t0 = time.perf_counter()
         e2e_run(args.steps)
         torch.cuda.synchronize(dev)
         e2e_s = (time.perf_counter() - t0) / args.steps
-        if sampler:
-            sampler.period_s = 0.002
         h2d_per_step, d2h_per_step = pipe.h2d_bytes // args.steps, pipe.d2h_bytes // args.steps
         clocks = sampler.stop() if sampler else None   # sampled over the three timed regions above (device-timed, stages, e2e)
 
