@@ -203,9 +203,12 @@ int nws_get_stage_times(NwsHandle handle, float* ms_out, int n);
  * h_generator (neural_waveshaping.py:69-72,78,82; shaping.py:68) — the whole hop-rate chain. */
 int nws_stage_control_to_params(NwsHandle handle, const float* control, int ctrl_channels, float* film_out,
                                 float* bands_out, int B, int T, void* workspace, size_t workspace_bytes, void* stream);
-/* Pipelined forward (default on): the GRU runs in 128-frame time blocks on an internal stream while the
- * caller's stream renders the blocks already encoded (MLP chain, noise hops, audio hops); used when the
- * batch is large enough (B*T >= 4096, T >= 129).  0 = strictly serial kernels on the caller's stream. */
+/* Pipelined forward (default on): the GRU runs on an internal stream while the caller's stream (and an auxiliary one)
+ * render, block by block in time, the frames already encoded (MLP chain, noise hops, audio hops); used when the batch is
+ * large enough (B*T >= 4096, T >= 257).  fp32 recurrence: a 128-frame head and the rest, one GRU launch each, stream events.
+ * Tensor-core recurrence: one GRU launch that publishes its progress in device-side counters, blocks of 32 then 117 frames,
+ * the consumers wait with a one-thread kernel (inside a stream capture: per-block launches and events instead).
+ * 0 = strictly serial kernels on the caller's stream. */
 int nws_set_pipeline(NwsHandle handle, int enable);
 
 /* Implementation of the GRU recurrence (ControlModule, neural_waveshaping.py:17-26): 1 (default) = tensor cores from 64
