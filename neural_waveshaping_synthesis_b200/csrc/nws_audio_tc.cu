@@ -865,12 +865,15 @@ int launch_variant(const NwsAudioParams& p, const float* wu, int* fault, int gri
   if (nws_first_use_on_device(attr_done))
     NWS_CUDA_OK(cudaFuncSetAttribute(nws_audio_tc_kernel<USE_LUT, TAP, MODE, SHP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TcCfg<USE_LUT>::kBytes));
+  // the noise branch's area (the last of the layout) is only paid for when that branch runs in this kernel: what is not
+  // shared memory is L1 for the table gathers
+  const int smem_bytes = p.bands ? TcCfg<USE_LUT>::kBytes : TcCfg<USE_LUT>::oNoise;
   if (!pdl) {
-    nws_audio_tc_kernel<USE_LUT, TAP, MODE, SHP><<<grid, kTcThreads, TcCfg<USE_LUT>::kBytes, s>>>(p, wu, fault);
+    nws_audio_tc_kernel<USE_LUT, TAP, MODE, SHP><<<grid, kTcThreads, smem_bytes, s>>>(p, wu, fault);
     return NWS_OK;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = TcCfg<USE_LUT>::kBytes; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   int n_attr = 0;
   nws_pdl_config(&cfg, attr, &n_attr, true);
