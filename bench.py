@@ -330,7 +330,7 @@ def lane_throughput_ms(model, dev, make_inputs, k, n_sets):
         for i in range(n):
             f0, control = sets[(first + i) % n_sets]
             with torch.cuda.stream(streams[i % LANES]):
-                outs[i % len(outs)] = model._forward_lane(i % LANES, f0, control, out=outs[i % len(outs)])
+                outs[i % len(outs)] = model.forward_lane(i % LANES, f0, control, out=outs[i % len(outs)])
 
     with torch.no_grad():
         for st in streams:

@@ -232,12 +232,17 @@ class NeuralWaveshaping(nn.Module):
         torch.initial_seed()."""
         if not isinstance(f0, torch.Tensor) or not isinstance(control, torch.Tensor):
             raise TypeError("f0 and control must be tensors")
-        return self._forward_lane(0, f0, control, phase_shift, noise)
+        return self.forward_lane(0, f0, control, phase_shift, noise)
 
-    def _forward_lane(self, lane, f0, control, phase_shift=None, noise=None, out=None):
-        """forward() through engine `lane` of the input's device (lane 0 = the one every other entry point uses)."""
+    def forward_lane(self, lane, f0, control, phase_shift=None, noise=None, out=None):
+        """forward() through engine `lane` of the input's device (lane 0 = the one every other entry point uses; extension,
+        not in the reference).  A lane is an independent C context — streams, workspace, scheduler counters — so forwards
+        issued on different lanes from different CUDA streams run concurrently (streaming.HostPipeline keeps two in
+        flight); forwards on one lane must be issued on one stream at a time.  `out`: optional result buffer [B, 128*T]."""
         eng = self._engine_for(f0, lane)
         return eng.forward(f0, control, u_phase=phase_shift, noise=noise, use_lut=isinstance(self.newt, FastNEWT), out=out)
+
+    _forward_lane = forward_lane
 
     def synthesise_from_host(self, f0, control, out=None, phase_shift=None, noise=None):
         """Host tensors in, host tensor out through nws_forward_host (H2D, forward, D2H, sync)."""

@@ -83,7 +83,7 @@ class HostPipeline:
                     cs.wait_event(ready)
                     if landed[slot] is not None:
                         cs.wait_event(landed[slot])    # the download that last read this output buffer
-                    self.model._forward_lane(lane, f0, control, out=y)
+                    self.model.forward_lane(lane, f0, control, out=y)
                     d = torch.cuda.Event()
                     d.record(cs)
                 done[slot] = d
